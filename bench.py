@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py - pairs/sec of PWC-Net's warp + cost-volume hot path on B200 (BASELINE.json metric).
+
+One "step" = one pass of the pyramid loop's hot path (tfoptflow/model_pwcnet.py:1550-1567: 5 cost volumes,
+4 warps) over one batch of synthetic feature pyramids.  Default workload = BASELINE.json configs[2]:
+Sintel 436x1024 padded to 448x1024, batch 32 per GPU, search_range 4, fp32, forward.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--dtype fp32|fp16] [--impl ours|reference]
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...       (one rank per GPU, weak scaling)
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` goes through the C ABI's
+host-buffer entry point with H2D/D2H inside the timed region, `roofline` is the dominant kernel (pyramid
+level 2) against the measured HBM copy bandwidth, `cpu_baseline` is the op-for-op CPU port of the
+reference graph (TensorFlow 1.10 is not installable) on the box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "pairs/sec for PWC-Net costvol+warp at 436x1024 (padded 448x1024)"
+UNIT = "pairs/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "fp16"])
+    ap.add_argument("--batch", type=int, default=32, help="pairs per GPU per step")
+    ap.add_argument("--height", type=int, default=448)
+    ap.add_argument("--width", type=int, default=1024)
+    ap.add_argument("--search-range", type=int, default=4)
+    ap.add_argument("--flow", default="smooth", choices=["smooth", "stress", "zero"])
+    ap.add_argument("--fwd-impl", type=int, default=0, help="library option fwd_impl (0 = auto)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 20)")
+    ap.add_argument("--per-level", action="store_true", help="also print per-level timings to stderr")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def roofline_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons with NVML every few ms while the timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.004):
+        self.index, self.period, self.samples, self.reasons = index, period_s, [], set()
+        self.max_mhz, self._stop, self._th, self.ok = None, threading.Event(), None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as e:  # NVML missing: report it, do not fail the bench
+            self.err = repr(e)
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+                 "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80)}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(get_reasons(self.h))
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def __enter__(self):
+        if self.ok:
+            self._th = threading.Thread(target=self._loop, daemon=True)
+            self._th.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._th:
+            self._th.join(timeout=1.0)
+
+    def summary(self):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "error": getattr(self, "err", "nvml unavailable")}
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def np_dtype(name):
+    return np.float32 if name == "fp32" else np.float16
+
+
+def workload_name(a):
+    return (f"BASELINE.json configs[2]: PWC-Net pyramid hot path (5 cost volumes L6..L2 + 4 warps L5..L2) on "
+            f"{a.height}x{a.width} (Sintel 436x1024 padded), batch {a.batch}/GPU, search_range {a.search_range}, "
+            f"{a.dtype}, forward")
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the reference graph's op-for-op port (oracle/ref_graph_torch.py) on the host cores
+# ------------------------------------------------------------------------------------------
+def cpu_port_time(a, batch, reps, budget_s):
+    import torch
+    from oracle import ref_graph_torch as T
+    from tfoptflow_b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    lv = synth.make_pyramid(batch, a.height, a.width, np.float32, flow=a.flow, search_range=a.search_range)
+    levels = [(torch.from_numpy(d["c1"]), torch.from_numpy(d["c2"]),
+               None if d["flow"] is None else torch.from_numpy(d["flow"]), d["scaler"]) for d in lv]
+    if a.dtype == "fp16":  # the reference's fp16 regime computes in fp16 on the CPU too
+        levels = [(c1.half(), c2.half(), None if f is None else f.half(), s) for c1, c2, f, s in levels]
+    times = []
+    t_end = time.perf_counter() + budget_s
+    with torch.no_grad():
+        for i in range(reps):
+            t0 = time.perf_counter()
+            T.pyramid_forward(levels, a.search_range)
+            times.append(time.perf_counter() - t0)
+            if time.perf_counter() > t_end and len(times) >= 2:
+                break
+    return times, torch.get_num_threads()
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sample_batch = 1
+    times, cores = cpu_port_time(a, sample_batch, a.warmup + a.steps, budget_s=240.0)
+    timed = times[a.warmup:] if len(times) > a.warmup else times[-1:]
+    ms = 1e3 * sum(timed) / len(timed)
+    val = sample_batch / (ms / 1e3)
+    sample = (f"{sample_batch} pair per step of the same workload ({a.height}x{a.width}, 5 levels, {a.dtype}), "
+              f"{len(timed)} timed steps, op-for-op torch-CPU port of the reference TF graph (TF 1.10 not installable)")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": len(timed),
+            "warmup": min(a.warmup, max(0, len(times) - len(timed))), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if a.dtype == "fp32" else "f16",
+            "data": "synthetic", "config": {"workload": workload_name(a), "sample_pairs_per_step": sample_batch},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from tfoptflow_b200 import _ffi, multi_gpus, pyramid, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU port)")
+    rank, world = multi_gpus.init_from_env()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = _ffi.load()
+    if a.fwd_impl:
+        _ffi.set_option("fwd_impl", a.fwd_impl)
+
+    ndt = np_dtype(a.dtype)
+    elt = 4 if a.dtype == "fp32" else 2
+    r = a.search_range
+    D = (2 * r + 1) ** 2
+    host_levels = synth.make_pyramid(a.batch, a.height, a.width, ndt, flow=a.flow, search_range=r)
+    dev_levels = []
+    for d in host_levels:
+        dev_levels.append({"lvl": d["lvl"], "c1": torch.from_numpy(d["c1"]).to(dev), "c2": torch.from_numpy(d["c2"]).to(dev),
+                           "flow": None if d["flow"] is None else torch.from_numpy(d["flow"]).to(dev),
+                           "scaler": d["scaler"]})
+    # one plan per level so the dominant kernel can be bracketed by events inside the timed region
+    plans = [pyramid.PyramidPlan([L], r) for L in dev_levels]
+    lvl_bytes = []
+    for d in host_levels:
+        b, h, w, c = d["c1"].shape
+        lvl_bytes.append(b * h * w * (2 * c + (2 if d["flow"] is not None else 0) + D) * elt)
+    dom = int(np.argmax(lvl_bytes))  # pyramid level 2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    stream = torch.cuda.current_stream(dev)
+    for _ in range(max(a.warmup, 3)):
+        for p in plans:
+            p.run()
+    torch.cuda.synchronize(dev)
+
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    lev = None
+    if a.per_level:
+        lev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in plans]
+               for _ in range(a.steps)]
+    launches0 = _ffi.launch_count()
+    sampler = ClockSampler(local)
+    barrier()
+    torch.cuda.synchronize(dev)
+    with sampler:
+        ev0.record(stream)
+        for s in range(a.steps):
+            for i, p in enumerate(plans):
+                if lev is not None:
+                    lev[s][i][0].record(stream)
+                elif i == dom:
+                    kev[s][0].record(stream)
+                p.run()
+                if lev is not None:
+                    lev[s][i][1].record(stream)
+                elif i == dom:
+                    kev[s][1].record(stream)
+        ev1.record(stream)
+        torch.cuda.synchronize(dev)
+    barrier()
+    launches = _ffi.launch_count() - launches0
+    ms_total = ev0.elapsed_time(ev1)
+    ms_step = ms_total / a.steps
+    if lev is not None:
+        per = [sum(lev[s][i][0].elapsed_time(lev[s][i][1]) for s in range(a.steps)) / a.steps for i in range(len(plans))]
+        dom_ms = per[dom]
+        if rank == 0:
+            for i, p in enumerate(per):
+                sys.stderr.write(f"[bench] level {host_levels[i]['lvl']}: {p * 1e3:9.1f} us  "
+                                 f"{lvl_bytes[i] / (p * 1e-3) / 1e9:8.1f} GB/s algorithmic\n")
+    else:
+        dom_ms = sum(k0.elapsed_time(k1) for k0, k1 in kev) / a.steps
+    if world > 1:
+        t = torch.tensor([ms_step, dom_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step, dom_ms = float(t[0]), float(t[1])
+    value = world * a.batch / (ms_step / 1e3)
+
+    peak, peak_src = peaks()
+    achieved = lvl_bytes[dom] / (dom_ms / 1e3) / 1e9
+    traffic = roofline_traffic().get(f"{a.dtype}_b{a.batch}_{a.height}x{a.width}")
+    fwd_pair_bytes = synth.fwd_bytes_per_pair(a.height, a.width, elt, r)
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "peak_source": peak_src, "kernel": f"fused warp+cost-volume fwd, pyramid level "
+            f"{host_levels[dom]['lvl']} ({host_levels[dom]['c1'].shape[1]}x{host_levels[dom]['c1'].shape[2]}x"
+            f"{host_levels[dom]['c1'].shape[3]})", "algorithmic_bytes_per_launch": lvl_bytes[dom],
+            "kernel_ms": dom_ms, "share_of_step": dom_ms / ms_step,
+            "whole_step_frac": (fwd_pair_bytes * a.batch / (ms_step / 1e3) / 1e9) / peak}
+
+    # ---- end to end through the host-buffer C ABI entry point ----
+    e2e = None
+    if not a.no_e2e:
+        def pinned(arr):
+            return torch.from_numpy(arr).pin_memory()
+        keep, hl, houts = [], [], []
+        for d in host_levels:
+            e = {"scaler": d["scaler"]}
+            for k in ("c1", "c2", "flow"):
+                if d[k] is None:
+                    e[k] = None
+                else:
+                    t = pinned(d[k])
+                    keep.append(t)
+                    e[k] = t.numpy()
+            hl.append(e)
+            b, h, w, c = d["c1"].shape
+            to = torch.empty((b, h, w, D), dtype=keep[-1].dtype, pin_memory=True)
+            keep.append(to)
+            houts.append(to.numpy())
+        hp = pyramid.HostPyramid()
+        h2d = sum(x.nbytes for e in hl for x in (e["c1"], e["c2"], e["flow"]) if x is not None)
+        d2h = sum(o.nbytes for o in houts)
+        n_e2e = a.e2e_steps or min(a.steps, 20)
+        for _ in range(3):
+            hp.run(hl, houts, r)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            hp.run(hl, houts, r)  # returns after the last D2H copy has completed
+        t_e2e = (time.perf_counter() - t0) / n_e2e
+        if world > 1:
+            t = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_e2e = float(t[0])
+        # spot check: the host path returns the same numbers as the device path
+        chk = float(np.abs(houts[dom].astype(np.float32) - plans[dom].outs[0].float().cpu().numpy()).max())
+        e2e = {"value": world * a.batch / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "steps": n_e2e, "ms_per_step": t_e2e * 1e3,
+               "max_abs_diff_vs_device_path": chk,
+               "path": "pwc_pyramid_fwd_host: pinned host buffers -> H2D -> kernels -> D2H, 3 streams"}
+        hp.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        times, cores = cpu_port_time(a, 1, 8, budget_s=25.0)
+        best = min(times[1:]) if len(times) > 1 else times[0]
+        cpu = {"value": 1.0 / best, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"1 pair of the same workload ({a.height}x{a.width}, 5 levels, {a.dtype}), best of "
+                         f"{max(1, len(times) - 1)} after 1 warm-up; op-for-op torch-CPU port of the reference TF graph"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32" if a.dtype == "fp32" else "f16", "data": "synthetic",
+                "config": {"workload": workload_name(a), "pairs_per_gpu_per_step": a.batch, "flow": a.flow,
+                           "l2_policy": f"inputs larger than L2: {fwd_pair_bytes * a.batch / 1e6:.0f} MB of distinct "
+                                        f"tensors stream through a 126 MB L2 every step",
+                           "fwd_impl": _ffi.get_option("fwd_impl"), "sharding": "batch-sharded, no collective"},
+                "clocks": sampler.summary(), "roofline": roof, "gpu_launches": int(launches)}
+        if e2e is not None:
+            line["e2e"] = e2e
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        return run_reference(a)
+    return run_ours(a)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,339 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C ABI
+(libpwc_b200.so via ctypes); the oracle (oracle/pwc_oracle.py) is only the checker.
+
+Tolerances (BASELINE.json north_star): fp32 1e-5 relative, fp16 mixed precision 1e-2; "relative" is
+taken element-wise with an absolute floor of tol * rms(reference), because cost-volume entries are sums
+with cancellation and can be arbitrarily close to zero."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pwc_oracle as O
+from tfoptflow_b200 import _ffi, cost_volume, dense_image_warp, pyramid, synth, warp_cost_volume
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+IMPLS = [1, 2, 3]  # generic, tiled, streaming (3 falls back to 2 where it does not apply)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    _ffi.load()
+    return torch.device("cuda", 0)
+
+
+@pytest.fixture(autouse=True)
+def _reset_impl():
+    yield
+    try:
+        _ffi.set_option("fwd_impl", 0)
+    except Exception:
+        pass
+
+
+def tol_of(dtype):
+    return 1e-5 if dtype in (np.float32, torch.float32) else 1e-2
+
+
+def assert_close(got, ref, tol, what=""):
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    if ref.size == 0:
+        return
+    rms = float(np.sqrt(np.mean(ref * ref)))
+    err = np.abs(got - ref)
+    bound = tol * np.abs(ref) + tol * max(rms, 1e-30)
+    bad = err > bound
+    assert not bad.any(), f"{what}: {int(bad.sum())}/{ref.size} elements off, max err {err.max():.3e}, rms {rms:.3e}"
+
+
+def to_dev(a, dev):
+    return None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def run_fwd(d, r, fs, dev, impl=0):
+    _ffi.set_option("fwd_impl", impl)
+    out = warp_cost_volume(to_dev(d["c1"], dev), to_dev(d["c2"], dev), to_dev(d.get("flow"), dev), r, fs)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+# ---------------------------------------------------------------- golden fixtures
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("path", GOLDEN, ids=lambda p: os.path.basename(p)[:-4])
+def test_golden_forward(path, impl, dev):
+    z = dict(np.load(path))
+    r, fs = int(z["r"]), float(z["flow_scale"])
+    out = run_fwd(z, r, fs, dev, impl)
+    assert out.dtype == z["out"].dtype
+    assert_close(out, z["out"], tol_of(z["out"].dtype.type), "fused fwd")
+    if "warp" in z:  # standalone ops at the two reference signatures
+        flow = to_dev(z["flow"], dev)
+        w = dense_image_warp(to_dev(z["c2"], dev), flow * fs, lazy=False)
+        if z["warp"].dtype == np.float32:
+            assert np.array_equal(w.cpu().numpy(), z["warp"]), "fp32 warp is bit-exact (same op order)"
+        else:
+            assert_close(w.cpu().numpy(), z["warp"], 1e-2, "warp")
+        cv = cost_volume(to_dev(z["c1"], dev), to_dev(z["warp"], dev), r, "corr")
+        assert_close(cv.cpu().numpy(), z["out"], tol_of(z["out"].dtype.type), "cost_volume(c1, warp)")
+
+
+@pytest.mark.parametrize("path", [p for p in GOLDEN if "f32" in p], ids=lambda p: os.path.basename(p)[:-4])
+def test_golden_backward(path, dev):
+    z = dict(np.load(path))
+    r, fs = int(z["r"]), float(z["flow_scale"])
+    c1, c2 = to_dev(z["c1"], dev).requires_grad_(), to_dev(z["c2"], dev).requires_grad_()
+    flow = to_dev(z["flow"], dev).requires_grad_() if "flow" in z else None
+    out = warp_cost_volume(c1, c2, flow, r, fs)
+    out.backward(to_dev(z["g"], dev))
+    torch.cuda.synchronize()
+    assert_close(c1.grad.cpu().numpy(), z["dc1"], 2e-5, "dc1")
+    assert_close(c2.grad.cpu().numpy(), z["dc2"], 2e-5, "dc2")
+    if flow is not None:
+        assert_close(flow.grad.cpu().numpy(), z["dflow"], 5e-5, "dflow")
+
+
+# ---------------------------------------------------------------- BASELINE configs[0]: 384x512, B=1, fp32
+@pytest.mark.parametrize("impl", IMPLS)
+def test_cfg0_all_levels_fp32(impl, dev):
+    for d in synth.make_pyramid(1, 384, 512, np.float32):
+        ref = O.warp_cost_volume(d["c1"], d["c2"], d["flow"], 4, d["scaler"])
+        assert_close(run_fwd(d, 4, d["scaler"], dev, impl), ref, 1e-5, f"level {d['lvl']}")
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_stress_flow_fp32(impl, dev):
+    for d in synth.make_pyramid(2, 192, 256, np.float32, flow="stress", levels=(5, 4, 3, 2)):
+        ref = O.warp_cost_volume(d["c1"], d["c2"], d["flow"], 4, d["scaler"])
+        assert_close(run_fwd(d, 4, d["scaler"], dev, impl), ref, 1e-5, f"level {d['lvl']}")
+
+
+# ---------------------------------------------------------------- BASELINE configs[1]: operator sweep, 6 levels, fwd+bwd
+def test_cfg1_operator_sweep_fwd_bwd(dev):
+    for d in synth.make_pyramid(4, 384, 512, np.float32, levels=(6, 5, 4, 3, 2, 1), top_has_flow=True, with_grad=True):
+        fs = d["scaler"]
+        c1, c2, flow = (to_dev(d[k], dev).requires_grad_() for k in ("c1", "c2", "flow"))
+        out = cost_volume(c1, dense_image_warp(c2, flow * fs), 4, f"corr{d['lvl']}")  # reference call pattern
+        out.backward(to_dev(d["g"], dev))
+        torch.cuda.synchronize()
+        scaled = d["flow"] * np.float32(fs)
+        ref = O.cost_volume(d["c1"], O.dense_image_warp(d["c2"], scaled), 4)
+        assert_close(out.detach().cpu().numpy(), ref, 1e-5, f"fwd level {d['lvl']}")
+        dc1, dc2, dflow = O.warp_cost_volume_bwd(d["g"], d["c1"], d["c2"], d["flow"], 4, fs)
+        assert_close(c1.grad.cpu().numpy(), dc1, 2e-5, f"dc1 level {d['lvl']}")
+        assert_close(c2.grad.cpu().numpy(), dc2, 2e-5, f"dc2 level {d['lvl']}")
+        assert_close(flow.grad.cpu().numpy(), dflow, 1e-4, f"dflow level {d['lvl']}")
+
+
+# ---------------------------------------------------------------- fp16 mixed precision
+@pytest.mark.parametrize("impl", IMPLS)
+def test_fp16_levels(impl, dev):
+    for d in synth.make_pyramid(2, 192, 256, np.float16):
+        ref = O.warp_cost_volume(d["c1"], d["c2"], d["flow"], 4, d["scaler"])
+        out = run_fwd(d, 4, d["scaler"], dev, impl)
+        assert out.dtype == np.float16
+        assert_close(out, ref, 1e-2, f"fp16 level {d['lvl']}")
+
+
+def test_fp16_backward(dev):
+    d = synth.make_level(2, 24, 32, 96, 77, np.float16, "smooth", with_grad=True)
+    c1, c2, flow = (to_dev(d[k], dev).requires_grad_() for k in ("c1", "c2", "flow"))
+    warp_cost_volume(c1, c2, flow, 4, 2.5).backward(to_dev(d["g"], dev))
+    f32 = {k: d[k].astype(np.float32) for k in ("c1", "c2", "flow", "g")}
+    dc1, dc2, dflow = O.warp_cost_volume_bwd(f32["g"], f32["c1"], f32["c2"], f32["flow"], 4, 2.5)
+    assert_close(c1.grad.float().cpu().numpy(), dc1, 2e-2, "dc1 fp16")
+    assert_close(c2.grad.float().cpu().numpy(), dc2, 2e-2, "dc2 fp16")
+    assert_close(flow.grad.float().cpu().numpy(), dflow, 5e-2, "dflow fp16")
+
+
+def test_bf16_extension(dev):
+    d = synth.make_level(1, 14, 32, 128, 78, np.float32, "smooth")
+    t = {k: to_dev(d[k], dev).bfloat16() for k in ("c1", "c2")}
+    t["flow"] = to_dev(d["flow"], dev)  # fp32 coordinates; bf16 would quantise them to 1/8 px
+    out = warp_cost_volume(t["c1"], t["c2"], t["flow"], 4, 1.25)
+    ref = O.warp_cost_volume(*(t[k].float().cpu().numpy() for k in ("c1", "c2", "flow")), 4, 1.25)
+    assert out.dtype == torch.bfloat16
+    assert_close(out.float().cpu().numpy(), ref, 4e-2, "bf16")
+
+
+# ---------------------------------------------------------------- edge cases the reference's contract implies
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("shape", [(1, 2, 2, 4), (1, 2, 3, 8), (3, 9, 11, 20), (1, 33, 65, 12), (2, 8, 32, 32),
+                                   (1, 7, 16, 196), (1, 13, 40, 5), (1, 5, 6, 3)])
+def test_ragged_shapes(shape, impl, dev):
+    b, h, w, c = shape
+    d = synth.make_level(b, h, w, c, 100 + h * w + c, np.float32, "stress")
+    ref = O.warp_cost_volume(d["c1"], d["c2"], d["flow"], 4, 0.625)
+    assert_close(run_fwd(d, 4, 0.625, dev, impl), ref, 1e-5, f"{shape}")
+    d["flow"] = None
+    assert_close(run_fwd(d, 4, 1.0, dev, impl), O.cost_volume(d["c1"], d["c2"], 4), 1e-5, f"{shape} no flow")
+
+
+@pytest.mark.parametrize("r", [0, 1, 2, 3, 5, 8])
+def test_other_search_ranges(r, dev):
+    d = synth.make_level(1, 10, 13, 8, 200 + r, np.float32, "smooth")
+    assert_close(run_fwd(d, r, 1.0, dev), O.warp_cost_volume(d["c1"], d["c2"], d["flow"], r), 1e-5, f"r={r}")
+
+
+def test_empty_batch(dev):
+    c = torch.empty((0, 8, 8, 16), device=dev)
+    out = warp_cost_volume(c, c, torch.empty((0, 8, 8, 2), device=dev), 4)
+    assert tuple(out.shape) == (0, 8, 8, 81)
+
+
+def test_huge_and_integer_flows(dev):
+    d = synth.make_level(1, 12, 16, 8, 300, np.float32, "zero")
+    for val in (1e4, -1e4, 1.0, -3.0, 0.0):
+        d["flow"] = np.full_like(d["flow"], val)
+        for impl in IMPLS:
+            assert_close(run_fwd(d, 4, 1.0, dev, impl), O.warp_cost_volume(d["c1"], d["c2"], d["flow"], 4), 1e-5,
+                         f"flow={val} impl={impl}")
+
+
+def test_zero_flow_backward_tie_rule(dev):
+    d = synth.make_level(1, 6, 8, 4, 8, np.float32, "zero", with_grad=True)
+    c1, c2, flow = (to_dev(d[k], dev).requires_grad_() for k in ("c1", "c2", "flow"))
+    warp_cost_volume(c1, c2, flow, 4).backward(to_dev(d["g"], dev))
+    _, _, dflow = O.warp_cost_volume_bwd(d["g"], d["c1"], d["c2"], d["flow"], 4)
+    g = flow.grad.cpu().numpy()
+    assert np.all(g[:, :-1, :, 0] == 0) and np.all(g[:, :, :-1, 1] == 0)
+    assert_close(g, dflow, 5e-5, "dflow at ties")
+
+
+def test_out_slice_of_concat_buffer(dev):
+    # model_pwcnet.py:1424 concatenates [corr, c1, up_flow, up_feat]; write corr straight into its slice
+    d = synth.make_level(2, 14, 32, 128, 400, np.float32, "smooth")
+    buf = torch.full((2, 14, 32, 81 + 128 + 2), -7.0, device=dev)
+    c1, c2, flow = (to_dev(d[k], dev) for k in ("c1", "c2", "flow"))
+    for impl in IMPLS:
+        buf.fill_(-7.0)
+        _ffi.set_option("fwd_impl", impl)
+        cost_volume(c1, dense_image_warp(c2, flow), 4, "corr5", out=buf[..., :81])
+        ref = O.warp_cost_volume(d["c1"], d["c2"], d["flow"], 4)
+        assert_close(buf[..., :81].cpu().numpy(), ref, 1e-5, "slice")
+        assert torch.all(buf[..., 81:] == -7.0)
+
+
+def test_non_contiguous_and_dlpack_inputs(dev):
+    d = synth.make_level(1, 12, 16, 16, 500, np.float32, "smooth")
+    c1 = to_dev(d["c1"], dev).permute(0, 3, 1, 2).contiguous().permute(0, 2, 3, 1)  # NHWC view of NCHW storage
+    assert not c1.is_contiguous()
+
+    class DL:  # any DLPack producer (TF2 eager / CuPy / JAX arrays look like this)
+        def __init__(self, t):
+            self.t = t
+
+        def __dlpack__(self, *a, **k):
+            return self.t.__dlpack__(*a, **k)
+
+        def __dlpack_device__(self):
+            return self.t.__dlpack_device__()
+
+    out = cost_volume(c1, dense_image_warp(DL(to_dev(d["c2"], dev)), DL(to_dev(d["flow"], dev))), 4, "corr")
+    assert_close(out.cpu().numpy(), O.warp_cost_volume(d["c1"], d["c2"], d["flow"], 4), 1e-5, "dlpack")
+
+
+def test_lazy_warp_materialises_for_other_consumers(dev):
+    d = synth.make_level(1, 12, 16, 16, 501, np.float32, "smooth")
+    w = dense_image_warp(to_dev(d["c2"], dev), to_dev(d["flow"], dev))
+    ref = O.dense_image_warp(d["c2"], d["flow"])
+    assert np.array_equal((w + 0).cpu().numpy(), ref)          # torch function
+    assert np.array_equal(torch.relu(w).cpu().numpy(), np.maximum(ref, 0))
+    assert tuple(w.shape) == ref.shape and w.dtype == torch.float32
+    assert np.array_equal(w.cpu().numpy(), ref)                   # method access
+    out = cost_volume(to_dev(d["c1"], dev), w, 4, "corr")         # already materialised: standalone kernel
+    assert_close(out.cpu().numpy(), O.cost_volume(d["c1"], ref, 4), 1e-5, "materialised")
+
+
+def test_error_behaviour(dev):
+    with pytest.raises(ValueError):
+        dense_image_warp(torch.zeros(4, 4, 4, device=dev), torch.zeros(1, 4, 4, 2, device=dev))
+    with pytest.raises(ValueError):
+        dense_image_warp(torch.zeros(1, 4, 4, 4, device=dev), torch.zeros(1, 4, 4, device=dev))
+    with pytest.raises(ValueError):
+        dense_image_warp(torch.zeros(1, 1, 4, 4, device=dev), torch.zeros(1, 1, 4, 2, device=dev))
+    with pytest.raises(ValueError):
+        cost_volume(torch.zeros(1, 4, 4, 4, device=dev), torch.zeros(1, 4, 5, 4, device=dev), 4, "x")
+    with pytest.raises(RuntimeError):
+        cost_volume(torch.zeros(1, 4, 4, 4), torch.zeros(1, 4, 4, 4), 4, "x")  # CPU tensors: no fallback
+    lib = _ffi.load()
+    assert lib.pwc_cost_volume_fwd(None, None, None, 1, 4, 4, 4, 4, 0, 0, None) == -1
+    assert b"null" in lib.pwc_last_error()
+    assert lib.pwc_warp_cost_volume_fwd(1, 1, 1, 1.0, 1, 1, 1, 4, 4, 4, 0, 0, 0, None) == -2  # H < 2 with a flow
+
+
+# ---------------------------------------------------------------- full BASELINE sizes: size-independent properties
+def _pyr_dev(b, h, w, dtype, dev, **k):
+    lv = synth.make_pyramid(b, h, w, dtype, **k)
+    return [{"lvl": d["lvl"], "scaler": d["scaler"], **{n: to_dev(d[n], dev) for n in ("c1", "c2", "flow")}} for d in lv]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float16])
+def test_cfg2_full_size_properties(dtype, dev):
+    """BASELINE configs[2]: 448x1024, batch 32.  Properties that need no CPU oracle at this size."""
+    lv = _pyr_dev(32, 448, 1024, dtype, dev)
+    plan = pyramid.PyramidPlan(lv, 4)
+    outs = [o.clone() for o in plan.run()]
+    torch.cuda.synchronize()
+    for L, o in zip(lv, outs):
+        c1, c2, flow, fs = L["c1"], L["c2"], L["flow"], L["scaler"]
+        assert torch.isfinite(o).all()
+        # (i) batch independence: a slice computed alone is bit-identical (no cross-sample term, row 8e)
+        sl = slice(5, 7)
+        alone = warp_cost_volume(c1[sl], c2[sl], None if flow is None else flow[sl], 4, fs)
+        assert torch.equal(alone, o[sl]), f"level {L['lvl']} batch independence"
+        # (ii) homogeneity: scaling c1 by 2 scales the output by exactly 2 (leaky-relu is positively homogeneous)
+        assert torch.equal(warp_cost_volume(c1[sl] * 2, c2[sl], None if flow is None else flow[sl], 4, fs), o[sl] * 2)
+        # (iii) centre channel of cost_volume(c1, c1) is mean_c(c1^2) (KAT 5)
+        cc = warp_cost_volume(c1[sl], c1[sl], None, 4)[..., 40].float()
+        ref = (c1[sl].float() ** 2).mean(-1)
+        tol = tol_of(dtype)
+        assert torch.all((cc - ref).abs() <= tol * ref.abs() + tol * ref.abs().mean())
+        # (iv) a sample against the oracle (2 pairs, every level)
+        ref = O.warp_cost_volume(c1[sl].cpu().numpy(), c2[sl].cpu().numpy(),
+                                 None if flow is None else flow[sl].cpu().numpy(), 4, fs)
+        assert_close(o[sl].cpu().numpy(), ref, tol, f"level {L['lvl']} vs oracle")
+    # (v) zero flow == no flow away from the last row/col (KAT 1) at full size, level 2
+    L = lv[-1]
+    z = warp_cost_volume(L["c1"][:4], L["c2"][:4], torch.zeros_like(L["flow"][:4]), 4, 5.0)
+    n = warp_cost_volume(L["c1"][:4], L["c2"][:4], None, 4)
+    assert_close(z.float().cpu().numpy(), n.float().cpu().numpy(), tol_of(dtype), "zero flow == no flow")
+    assert torch.equal(z[:, :-5, :-5], n[:, :-5, :-5])
+
+
+def test_cfg4_large_displacement_sample(dev):
+    """BASELINE configs[4]: search_range 8 (289 channels) at 1088x1920, fp16: level-2 shape (272x480x32) for
+    the size-independent properties, a smaller frame against the oracle (numpy fp16 is slow)."""
+    d = synth.make_level(2, 272, 480, 32, 1971, np.float16, "stress")
+    c1, c2, flow = (to_dev(d[k], dev) for k in ("c1", "c2", "flow"))
+    out = warp_cost_volume(c1, c2, flow, 8, 5.0)
+    assert tuple(out.shape) == (2, 272, 480, 289) and torch.isfinite(out).all()
+    assert torch.equal(warp_cost_volume(c1[1:], c2[1:], flow[1:], 8, 5.0), out[1:])
+    assert torch.equal(warp_cost_volume(c1 * 2, c2, flow, 8, 5.0), out * 2)
+    s = synth.make_level(1, 34, 60, 32, 1972, np.float16, "stress")
+    ref = O.warp_cost_volume(s["c1"], s["c2"], s["flow"], 8, 5.0)
+    assert_close(run_fwd(s, 8, 5.0, dev), ref, 1e-2, "r=8 fp16")
+
+
+def test_host_buffer_path_matches_device_path(dev):
+    lv = synth.make_pyramid(3, 192, 256, np.float32)
+    outs = [np.empty(d["c1"].shape[:3] + (81,), np.float32) for d in lv]
+    hp = pyramid.HostPyramid()
+    hp.run(lv, outs, 4)
+    hp.run(lv, outs, 4)  # second call reuses the cached scratch
+    hp.close()
+    for d, o in zip(lv, outs):
+        assert_close(o, O.warp_cost_volume(d["c1"], d["c2"], d["flow"], 4, d["scaler"]), 1e-5, f"host level {d['lvl']}")
+
+
+def test_launch_counter_proves_native_path(dev):
+    before = _ffi.launch_count()
+    d = synth.make_level(1, 8, 8, 8, 1, np.float32, "smooth")
+    run_fwd(d, 4, 1.0, dev)
+    assert _ffi.launch_count() == before + 1

@@ -1,0 +1,147 @@
+// Backward kernels (v1): what TF 1.10 autodiff emits for cost_volume / dense_image_warp
+// (SURVEY.md section 8a row G), written as gather-form kernels plus one scatter for the warp.
+//   g'[p,d]    = g[p,d] * (out[p,d] > 0 ? 1 : 0.1)        (ties go to the 0.1 branch)
+//   dc1[p,c]   = 1/C * sum_d g'[p,d]   * warpZ[p+d,c]
+//   dwarp[q,c] = 1/C * sum_d g'[q-d,d] * c1[q-d,c]          (q-d inside the image)
+//   dc2        = scatter-add of dwarp with the 4 bilinear weights
+//   dflow      = -(d/dalpha . dwarp) * clamp-mask * flow_scale
+#pragma once
+#include "common.cuh"
+
+namespace pwc {
+
+template <int VEC> struct Vec { float v[VEC]; };
+
+template <int VEC, typename T>
+__device__ __forceinline__ Vec<VEC> ldv(const T* p) {
+  Vec<VEC> r;
+  if (VEC == 4) {
+    const float4 f = ld4(p);
+    r.v[0] = f.x; r.v[1 % VEC] = f.y; r.v[2 % VEC] = f.z; r.v[3 % VEC] = f.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) r.v[i] = ElemTraits<T>::to_f(p[i]);
+  }
+  return r;
+}
+template <int VEC, typename T>
+__device__ __forceinline__ void stv(T* p, const Vec<VEC>& r) {
+  if (VEC == 4) {
+    st4(p, make_float4(r.v[0], r.v[1 % VEC], r.v[2 % VEC], r.v[3 % VEC]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) p[i] = ElemTraits<T>::from_f(r.v[i]);
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ float gprime(const T* __restrict__ g, const T* __restrict__ out, size_t p, int d,
+                                        int64_t gps, int64_t ops) {
+  const float gv = ElemTraits<T>::to_f(g[p * gps + d]);
+  const float ov = ElemTraits<T>::to_f(out[p * ops + d]);
+  return gv * (ov > 0.0f ? 1.0f : 0.1f);
+}
+
+// MODE 0: dc1[p,c]   (other = warp, reads other[p+d])
+// MODE 1: dwarp[q,c] (other = c1,   reads g'[q-d,d] and other[q-d])
+template <int MODE, int VEC, typename T, typename TO>
+__global__ void __launch_bounds__(256)
+bwd_corr_kernel(const T* __restrict__ g, const T* __restrict__ out, const T* __restrict__ other,
+                TO* __restrict__ dst, int B, int H, int W, int C, int r, int64_t gps, int64_t ops) {
+  const int n = 2 * r + 1;
+  const int CV = C / VEC;
+  const int64_t total = (int64_t)B * H * W * CV;
+  const float inv_c = 1.0f / (float)C;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % CV) * VEC;
+    const int64_t p = idx / CV;
+    const int x = (int)(p % W), y = (int)((p / W) % H), b = (int)(p / ((int64_t)W * H));
+    Vec<VEC> acc;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc.v[i] = 0.0f;
+    for (int dyi = 0; dyi < n; ++dyi) {
+      const int yy = MODE == 0 ? y + dyi - r : y - (dyi - r);
+      if (yy < 0 || yy >= H) continue;
+      for (int dxi = 0; dxi < n; ++dxi) {
+        const int xx = MODE == 0 ? x + dxi - r : x - (dxi - r);
+        if (xx < 0 || xx >= W) continue;
+        const size_t pp = ((size_t)b * H + yy) * W + xx;
+        const float gp = gprime<T>(g, out, MODE == 0 ? (size_t)p : pp, dyi * n + dxi, gps, ops);
+        const Vec<VEC> o = ldv<VEC, T>(other + pp * C + c);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc.v[i] = fmaf(gp, o.v[i], acc.v[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc.v[i] *= inv_c;
+    stv<VEC, TO>(dst + (size_t)p * C + c, acc);
+  }
+}
+
+// dense_image_warp backward: one warp per output pixel, lanes stride over channels.
+// dimg_acc is an fp32 accumulator (zero-initialised by the caller); dflow gets -(dalpha)*mask*scale.
+template <int VEC, typename T, typename TF, typename TG>
+__global__ void __launch_bounds__(256)
+warp_bwd_kernel(const TG* __restrict__ gout, const T* __restrict__ img, const TF* __restrict__ flow,
+                float flow_scale, float* __restrict__ dimg_acc, TF* __restrict__ dflow,
+                int B, int H, int W, int C) {
+  const int lane = threadIdx.x & 31;
+  const int64_t npix = (int64_t)B * H * W;
+  const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < npix; p += warps_total) {
+    const int x = (int)(p % W), y = (int)((p / W) % H), b = (int)(p / ((int64_t)W * H));
+    const SampleCoord s = sample_coord<T, TF>(flow, flow_scale, b, y, x, H, W);
+    const float ax = s.ax, ay = s.ay;
+    const float w_tl = (1.f - ay) * (1.f - ax), w_tr = (1.f - ay) * ax, w_bl = ay * (1.f - ax), w_br = ay * ax;
+    float dax = 0.f, day = 0.f;
+    const size_t i_tl = (size_t)s.pix * C, i_tr = i_tl + C, i_bl = i_tl + (size_t)W * C, i_br = i_bl + C;
+    for (int c = lane * VEC; c < C; c += 32 * VEC) {
+      const Vec<VEC> gw = ldv<VEC, TG>(gout + (size_t)p * C + c);
+      const Vec<VEC> tl = ldv<VEC, T>(img + i_tl + c), tr = ldv<VEC, T>(img + i_tr + c);
+      const Vec<VEC> bl = ldv<VEC, T>(img + i_bl + c), br = ldv<VEC, T>(img + i_br + c);
+      if (VEC == 4) {
+        atomicAdd(reinterpret_cast<float4*>(dimg_acc + i_tl + c),
+                  make_float4(gw.v[0] * w_tl, gw.v[1 % VEC] * w_tl, gw.v[2 % VEC] * w_tl, gw.v[3 % VEC] * w_tl));
+        atomicAdd(reinterpret_cast<float4*>(dimg_acc + i_tr + c),
+                  make_float4(gw.v[0] * w_tr, gw.v[1 % VEC] * w_tr, gw.v[2 % VEC] * w_tr, gw.v[3 % VEC] * w_tr));
+        atomicAdd(reinterpret_cast<float4*>(dimg_acc + i_bl + c),
+                  make_float4(gw.v[0] * w_bl, gw.v[1 % VEC] * w_bl, gw.v[2 % VEC] * w_bl, gw.v[3 % VEC] * w_bl));
+        atomicAdd(reinterpret_cast<float4*>(dimg_acc + i_br + c),
+                  make_float4(gw.v[0] * w_br, gw.v[1 % VEC] * w_br, gw.v[2 % VEC] * w_br, gw.v[3 % VEC] * w_br));
+      } else {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          atomicAdd(dimg_acc + i_tl + c + i, gw.v[i] * w_tl);
+          atomicAdd(dimg_acc + i_tr + c + i, gw.v[i] * w_tr);
+          atomicAdd(dimg_acc + i_bl + c + i, gw.v[i] * w_bl);
+          atomicAdd(dimg_acc + i_br + c + i, gw.v[i] * w_br);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const float top = ax * (tr.v[i] - tl.v[i]) + tl.v[i];
+        const float bot = ax * (br.v[i] - bl.v[i]) + bl.v[i];
+        dax = fmaf(gw.v[i], (1.f - ay) * (tr.v[i] - tl.v[i]) + ay * (br.v[i] - bl.v[i]), dax);
+        day = fmaf(gw.v[i], bot - top, day);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      dax += __shfl_xor_sync(0xffffffffu, dax, o);
+      day += __shfl_xor_sync(0xffffffffu, day, o);
+    }
+    if (lane == 0) {
+      dflow[2 * p] = ElemTraits<TF>::from_f(-day * s.my * flow_scale);
+      dflow[2 * p + 1] = ElemTraits<TF>::from_f(-dax * s.mx * flow_scale);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) cast_from_f32_kernel(const float* __restrict__ src, T* __restrict__ dst, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = ElemTraits<T>::from_f(src[i]);
+}
+
+}  // namespace pwc

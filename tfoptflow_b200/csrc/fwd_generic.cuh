@@ -1,0 +1,71 @@
+// Generic (any C, any r, any alignment) forward kernels: the correctness baseline on the GPU and
+// the path for shapes the tuned kernels do not cover.  One thread per output element.
+#pragma once
+#include "common.cuh"
+
+namespace pwc {
+
+// out[p, d] = lrelu( 1/C * sum_c c1[p,c] * warpZ[p+d, c] ), warp evaluated on the fly.
+template <typename T, typename TF>
+__global__ void __launch_bounds__(256)
+fwd_generic_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* __restrict__ flow,
+                   float flow_scale, T* __restrict__ out, int B, int H, int W, int C, int r,
+                   int64_t out_pixel_stride) {
+  const int n = 2 * r + 1, D = n * n;
+  const int64_t total = (int64_t)B * H * W * D;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int d = (int)(idx % D);
+    const int64_t p = idx / D;
+    const int x = (int)(p % W), y = (int)((p / W) % H), b = (int)(p / ((int64_t)W * H));
+    const int dy = d / n - r, dx = d % n - r;
+    const int yy = y + dy, xx = x + dx;
+    float acc = 0.0f;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+      const T* a = c1 + (size_t)p * C;
+      if (flow != nullptr) {
+        const SampleCoord s = sample_coord<T, TF>(flow, flow_scale, b, yy, xx, H, W);
+        for (int c = 0; c < C; ++c) acc = fmaf(ElemTraits<T>::to_f(a[c]), sample1<T>(c2, s, W, C, c), acc);
+      } else {
+        const T* w = c2 + (((size_t)b * H + yy) * W + xx) * C;
+        for (int c = 0; c < C; ++c) acc = fmaf(ElemTraits<T>::to_f(a[c]), ElemTraits<T>::to_f(w[c]), acc);
+      }
+    }
+    out[(size_t)p * out_pixel_stride + d] = ElemTraits<T>::from_f(lrelu01(acc * (1.0f / (float)C)));
+  }
+}
+
+// dense_image_warp forward, one thread per (pixel, channel)
+template <typename T, typename TF>
+__global__ void __launch_bounds__(256)
+warp_fwd_scalar_kernel(const T* __restrict__ img, const TF* __restrict__ flow, float flow_scale,
+                       T* __restrict__ out, int B, int H, int W, int C) {
+  const int64_t total = (int64_t)B * H * W * C;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const int64_t p = idx / C;
+    const int x = (int)(p % W), y = (int)((p / W) % H), b = (int)(p / ((int64_t)W * H));
+    const SampleCoord s = sample_coord<T, TF>(flow, flow_scale, b, y, x, H, W);
+    out[idx] = ElemTraits<T>::from_f(sample1<T>(img, s, W, C, c));
+  }
+}
+
+// dense_image_warp forward, one thread per (pixel, 4 channels); needs C % 4 == 0 and aligned pointers
+template <typename T, typename TF>
+__global__ void __launch_bounds__(256)
+warp_fwd_vec4_kernel(const T* __restrict__ img, const TF* __restrict__ flow, float flow_scale,
+                     T* __restrict__ out, int B, int H, int W, int C) {
+  const int C4 = C >> 2;
+  const int64_t total = (int64_t)B * H * W * C4;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C4) * 4;
+    const int64_t p = idx / C4;
+    const int x = (int)(p % W), y = (int)((p / W) % H), b = (int)(p / ((int64_t)W * H));
+    const SampleCoord s = sample_coord<T, TF>(flow, flow_scale, b, y, x, H, W);
+    st4(out + (size_t)p * C + c, sample4<T>(img, s, W, C, c));
+  }
+}
+
+}  // namespace pwc

@@ -1,0 +1,553 @@
+// C ABI of libpwc_b200.so (see include/pwc_b200.h).  Host-side dispatch only; kernels live in *.cuh.
+#include "../../include/pwc_b200.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "bwd.cuh"
+#include "common.cuh"
+#include "fwd_generic.cuh"
+#include "fwd_tile.cuh"
+#ifdef PWC_HAVE_STREAM_KERNEL
+#include "fwd_stream.cuh"
+#endif
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_fwd_impl{0};
+std::atomic<int> g_stream_ctas{0};
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define PWC_CUDA(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t e__ = (expr);                                                                  \
+    if (e__ != cudaSuccess) return fail(PWC_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+#define PWC_LAUNCH_CHECK()                                                                      \
+  do {                                                                                          \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                         \
+    cudaError_t e__ = cudaGetLastError();                                                       \
+    if (e__ != cudaSuccess) return fail(PWC_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e__)); \
+  } while (0)
+
+struct DevInfo {
+  int major = -1, minor = 0, sms = 0;
+};
+DevInfo g_dev[64];
+std::mutex g_dev_mu;
+
+int device_info(DevInfo* out) {
+  int dev = 0;
+  PWC_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(PWC_ERR_ARCH, "device index %d out of range", dev);
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  if (g_dev[dev].major < 0) {
+    DevInfo d;
+    PWC_CUDA(cudaDeviceGetAttribute(&d.major, cudaDevAttrComputeCapabilityMajor, dev));
+    PWC_CUDA(cudaDeviceGetAttribute(&d.minor, cudaDevAttrComputeCapabilityMinor, dev));
+    PWC_CUDA(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+    g_dev[dev] = d;
+  }
+  *out = g_dev[dev];
+  if (out->major != 10)
+    return fail(PWC_ERR_ARCH, "libpwc_b200 is built for sm_100a only; device %d is sm_%d%d (no fallback path)", dev,
+                out->major, out->minor);
+  return PWC_OK;
+}
+
+size_t elt_size(int dtype) { return dtype == PWC_F32 ? 4 : 2; }
+bool dtype_ok(int dtype) { return dtype == PWC_F32 || dtype == PWC_F16 || dtype == PWC_BF16; }
+bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+size_t up256(size_t n) { return (n + 255) & ~size_t(255); }
+
+int check_shape(int B, int H, int W, int C, int r, bool has_flow) {
+  if (B < 0 || H < 0 || W < 0 || C <= 0 || r < 0) return fail(PWC_ERR_BAD_SHAPE, "negative dimension");
+  if ((int64_t)B * H * W >= (int64_t)1 << 31) return fail(PWC_ERR_BAD_SHAPE, "B*H*W must be < 2^31");
+  if (has_flow && (H < 2 || W < 2))
+    return fail(PWC_ERR_BAD_SHAPE, "dense_image_warp needs height >= 2 and width >= 2 (got %dx%d)", H, W);
+  if (r > 64) return fail(PWC_ERR_BAD_SHAPE, "search_range %d too large", r);
+  return PWC_OK;
+}
+
+int grid_for(int64_t total, int block, int sms) {
+  int64_t g = (total + block - 1) / block;
+  const int64_t cap = (int64_t)sms * 32;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ---- forward dispatch ----------------------------------------------------------------
+template <typename T, typename TF>
+int fwd_typed(const void* c1, const void* c2, const void* flow, float flow_scale, void* out, int B, int H, int W,
+              int C, int r, int64_t ops, cudaStream_t st, const DevInfo& dev) {
+  const int n = 2 * r + 1;
+  const int64_t D = (int64_t)n * n;
+  if (ops == 0) ops = D;
+  if (ops < D) return fail(PWC_ERR_BAD_ARG, "out_pixel_stride %lld < (2r+1)^2", (long long)ops);
+  if ((int64_t)B * H * W == 0) return PWC_OK;
+  const size_t va = sizeof(T) * 4;  // vector alignment for 4-element loads
+  const bool vec_ok = (C % 4 == 0) && aligned(c1, va) && aligned(c2, va);
+  int impl = g_fwd_impl.load();
+  if (impl == 0) impl = (r == 4 && vec_ok) ? 2 : 1;
+  if (impl >= 2 && !(r == 4 && vec_ok)) impl = 1;
+#ifdef PWC_HAVE_STREAM_KERNEL
+  if (impl == 3) {
+    int rc = pwc::stream::launch<T, TF>((const T*)c1, (const T*)c2, (const TF*)flow, flow_scale, (T*)out, B, H, W, C,
+                                        ops, st, dev.sms, g_stream_ctas.load());
+    if (rc == 0) { PWC_LAUNCH_CHECK(); return PWC_OK; }
+    if (rc < 0) return fail(PWC_ERR_CUDA, "stream kernel launch failed");
+    impl = 2;  // rc > 0: shape not covered
+  }
+#else
+  if (impl == 3) impl = 2;
+#endif
+  if (impl == 2) {
+    using K = pwc::tile::Cfg<4>;
+    auto kern = pwc::tile::fwd_tile_kernel<4, T, TF>;
+    static std::atomic<uint64_t> attr_set{0};  // per (T,TF) instantiation; one bit per device
+    int devid = 0;
+    PWC_CUDA(cudaGetDevice(&devid));
+    if (!((attr_set.load() >> devid) & 1)) {
+      PWC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
+      attr_set.fetch_or(uint64_t(1) << devid);
+    }
+    const int tiles_x = (W + K::TW - 1) / K::TW, tiles_y = (H + K::TH - 1) / K::TH;
+    const int64_t tiles = (int64_t)tiles_x * tiles_y * B;
+    if (tiles >= (int64_t)1 << 31) return fail(PWC_ERR_BAD_SHAPE, "too many tiles");
+    kern<<<(unsigned)tiles, K::NTHREADS, K::SMEM_BYTES, st>>>((const T*)c1, (const T*)c2, (const TF*)flow, flow_scale,
+                                                             (T*)out, B, H, W, C, ops, tiles_x, tiles_y);
+    PWC_LAUNCH_CHECK();
+    return PWC_OK;
+  }
+  const int64_t total = (int64_t)B * H * W * D;
+  pwc::fwd_generic_kernel<T, TF><<<grid_for(total, 256, dev.sms), 256, 0, st>>>(
+      (const T*)c1, (const T*)c2, (const TF*)flow, flow_scale, (T*)out, B, H, W, C, r, ops);
+  PWC_LAUNCH_CHECK();
+  return PWC_OK;
+}
+
+template <typename... A>
+int fwd_dispatch(int dtype, int flow_dtype, const void* flow, A... a) {
+  // flow dtype must be the feature dtype or fp32 (the reference allows any mix; these are the ones it uses)
+  if (flow == nullptr) flow_dtype = dtype;
+  if (dtype == PWC_F32 && flow_dtype == PWC_F32) return fwd_typed<float, float>(a...);
+  if (dtype == PWC_F16 && flow_dtype == PWC_F16) return fwd_typed<__half, __half>(a...);
+  if (dtype == PWC_F16 && flow_dtype == PWC_F32) return fwd_typed<__half, float>(a...);
+  if (dtype == PWC_BF16 && flow_dtype == PWC_BF16) return fwd_typed<__nv_bfloat16, __nv_bfloat16>(a...);
+  if (dtype == PWC_BF16 && flow_dtype == PWC_F32) return fwd_typed<__nv_bfloat16, float>(a...);
+  return fail(PWC_ERR_BAD_DTYPE, "unsupported (feature dtype %d, flow dtype %d) combination", dtype, flow_dtype);
+}
+
+int fwd_entry(const void* c1, const void* c2, const void* flow, float flow_scale, void* out, int B, int H, int W,
+              int C, int r, int dtype, int flow_dtype, int64_t ops, void* stream) {
+  if (!dtype_ok(dtype) || (flow && !dtype_ok(flow_dtype))) return fail(PWC_ERR_BAD_DTYPE, "unknown dtype");
+  int rc = check_shape(B, H, W, C, r, flow != nullptr);
+  if (rc) return rc;
+  if ((int64_t)B * H * W > 0 && (!c1 || !c2 || !out)) return fail(PWC_ERR_BAD_ARG, "null tensor pointer");
+  if (!aligned(c1, elt_size(dtype)) || !aligned(c2, elt_size(dtype)) || !aligned(out, elt_size(dtype)) ||
+      (flow && !aligned(flow, elt_size(flow_dtype))))
+    return fail(PWC_ERR_ALIGN, "tensor pointer not aligned to its element size");
+  DevInfo dev;
+  rc = device_info(&dev);
+  if (rc) return rc;
+  return fwd_dispatch(dtype, flow_dtype, flow, c1, c2, flow, flow_scale, out, B, H, W, C, r, ops,
+                      (cudaStream_t)stream, dev);
+}
+
+// ---- standalone warp -------------------------------------------------------------------
+template <typename T, typename TF>
+int warp_fwd_typed(const void* img, const void* flow, float scale, void* out, int B, int H, int W, int C,
+                   cudaStream_t st, const DevInfo& dev) {
+  if ((int64_t)B * H * W == 0) return PWC_OK;
+  const size_t va = sizeof(T) * 4;
+  if (C % 4 == 0 && aligned(img, va) && aligned(out, va)) {
+    const int64_t total = (int64_t)B * H * W * (C / 4);
+    pwc::warp_fwd_vec4_kernel<T, TF><<<grid_for(total, 256, dev.sms), 256, 0, st>>>((const T*)img, (const TF*)flow,
+                                                                                   scale, (T*)out, B, H, W, C);
+  } else {
+    const int64_t total = (int64_t)B * H * W * C;
+    pwc::warp_fwd_scalar_kernel<T, TF><<<grid_for(total, 256, dev.sms), 256, 0, st>>>((const T*)img, (const TF*)flow,
+                                                                                     scale, (T*)out, B, H, W, C);
+  }
+  PWC_LAUNCH_CHECK();
+  return PWC_OK;
+}
+
+int warp_fwd_entry(const void* img, const void* flow, float scale, void* out, int B, int H, int W, int C, int dtype,
+                   int flow_dtype, cudaStream_t st) {
+  if (!dtype_ok(dtype) || !dtype_ok(flow_dtype)) return fail(PWC_ERR_BAD_DTYPE, "unknown dtype");
+  int rc = check_shape(B, H, W, C, 0, true);
+  if (rc) return rc;
+  if ((int64_t)B * H * W > 0 && (!img || !flow || !out)) return fail(PWC_ERR_BAD_ARG, "null tensor pointer");
+  if (!aligned(img, elt_size(dtype)) || !aligned(out, elt_size(dtype)) || !aligned(flow, elt_size(flow_dtype)))
+    return fail(PWC_ERR_ALIGN, "tensor pointer not aligned to its element size");
+  DevInfo dev;
+  rc = device_info(&dev);
+  if (rc) return rc;
+  if (dtype == PWC_F32 && flow_dtype == PWC_F32) return warp_fwd_typed<float, float>(img, flow, scale, out, B, H, W, C, st, dev);
+  if (dtype == PWC_F16 && flow_dtype == PWC_F16) return warp_fwd_typed<__half, __half>(img, flow, scale, out, B, H, W, C, st, dev);
+  if (dtype == PWC_F16 && flow_dtype == PWC_F32) return warp_fwd_typed<__half, float>(img, flow, scale, out, B, H, W, C, st, dev);
+  if (dtype == PWC_BF16 && flow_dtype == PWC_BF16) return warp_fwd_typed<__nv_bfloat16, __nv_bfloat16>(img, flow, scale, out, B, H, W, C, st, dev);
+  if (dtype == PWC_BF16 && flow_dtype == PWC_F32) return warp_fwd_typed<__nv_bfloat16, float>(img, flow, scale, out, B, H, W, C, st, dev);
+  return fail(PWC_ERR_BAD_DTYPE, "unsupported (image dtype %d, flow dtype %d) combination", dtype, flow_dtype);
+}
+
+// ---- backward --------------------------------------------------------------------------
+template <int MODE, typename T, typename TO>
+int bwd_corr_launch(const void* g, const void* out, const void* other, void* dst, int B, int H, int W, int C, int r,
+                    int64_t gps, int64_t ops, cudaStream_t st, const DevInfo& dev) {
+  const size_t va = sizeof(T) * 4;
+  if (C % 4 == 0 && aligned(other, va) && aligned(dst, sizeof(TO) * 4)) {
+    const int64_t total = (int64_t)B * H * W * (C / 4);
+    pwc::bwd_corr_kernel<MODE, 4, T, TO><<<grid_for(total, 256, dev.sms), 256, 0, st>>>(
+        (const T*)g, (const T*)out, (const T*)other, (TO*)dst, B, H, W, C, r, gps, ops);
+  } else {
+    const int64_t total = (int64_t)B * H * W * C;
+    pwc::bwd_corr_kernel<MODE, 1, T, TO><<<grid_for(total, 256, dev.sms), 256, 0, st>>>(
+        (const T*)g, (const T*)out, (const T*)other, (TO*)dst, B, H, W, C, r, gps, ops);
+  }
+  PWC_LAUNCH_CHECK();
+  return PWC_OK;
+}
+
+template <typename T, typename TF, typename TG>
+int warp_bwd_launch(const void* gout, const void* img, const void* flow, float scale, float* dimg_acc, void* dflow,
+                    int B, int H, int W, int C, cudaStream_t st, const DevInfo& dev) {
+  const int64_t npix = (int64_t)B * H * W;
+  const int grid = grid_for(npix * 32, 256, dev.sms);
+  if (C % 4 == 0 && aligned(gout, sizeof(TG) * 4) && aligned(img, sizeof(T) * 4) && aligned(dimg_acc, 16)) {
+    pwc::warp_bwd_kernel<4, T, TF, TG><<<grid, 256, 0, st>>>((const TG*)gout, (const T*)img, (const TF*)flow, scale,
+                                                            dimg_acc, (TF*)dflow, B, H, W, C);
+  } else {
+    pwc::warp_bwd_kernel<1, T, TF, TG><<<grid, 256, 0, st>>>((const TG*)gout, (const T*)img, (const TF*)flow, scale,
+                                                            dimg_acc, (TF*)dflow, B, H, W, C);
+  }
+  PWC_LAUNCH_CHECK();
+  return PWC_OK;
+}
+
+template <typename T>
+int cast_launch(const float* src, void* dst, int64_t n, cudaStream_t st, const DevInfo& dev) {
+  pwc::cast_from_f32_kernel<T><<<grid_for(n, 256, dev.sms), 256, 0, st>>>(src, (T*)dst, n);
+  PWC_LAUNCH_CHECK();
+  return PWC_OK;
+}
+
+struct BwdWs {
+  size_t warp_off, dwarp_off, acc_off, total;
+};
+BwdWs bwd_ws_layout(int B, int H, int W, int C, int dtype, bool has_flow) {
+  const size_t n = (size_t)B * H * W * C;
+  BwdWs w{};
+  size_t off = 0;
+  w.warp_off = off;
+  if (has_flow) off += up256(n * elt_size(dtype));
+  w.dwarp_off = off;
+  if (has_flow) off += up256(n * 4);
+  w.acc_off = off;
+  if (has_flow && dtype != PWC_F32) off += up256(n * 4);
+  w.total = off;
+  return w;
+}
+
+template <typename T>
+int cv_bwd_typed(const void* g, const void* out, const void* c1, const void* warp, void* dc1, void* dwarp, int B, int H,
+                 int W, int C, int r, int64_t gps, int64_t ops, cudaStream_t st, const DevInfo& dev) {
+  int rc = bwd_corr_launch<0, T, T>(g, out, warp, dc1, B, H, W, C, r, gps, ops, st, dev);
+  if (rc) return rc;
+  return bwd_corr_launch<1, T, T>(g, out, c1, dwarp, B, H, W, C, r, gps, ops, st, dev);
+}
+
+template <typename T, typename TF>
+int fused_bwd_typed(const void* g, const void* out, const void* c1, const void* c2, const void* flow, float scale,
+                    void* dc1, void* dc2, void* dflow, int B, int H, int W, int C, int r, int dtype, int64_t gps,
+                    int64_t ops, void* ws, size_t ws_bytes, cudaStream_t st, const DevInfo& dev) {
+  if (flow == nullptr) return cv_bwd_typed<T>(g, out, c1, c2, dc1, dc2, B, H, W, C, r, gps, ops, st, dev);
+  const BwdWs L = bwd_ws_layout(B, H, W, C, dtype, true);
+  if (ws_bytes < L.total || ws == nullptr)
+    return fail(PWC_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", L.total, ws_bytes);
+  if (!aligned(ws, 256)) return fail(PWC_ERR_ALIGN, "workspace must be 256-byte aligned");
+  char* base = (char*)ws;
+  void* wbuf = base + L.warp_off;
+  float* dwbuf = (float*)(base + L.dwarp_off);
+  const size_t n = (size_t)B * H * W * C;
+  int rc = warp_fwd_typed<T, TF>(c2, flow, scale, wbuf, B, H, W, C, st, dev);
+  if (rc) return rc;
+  rc = bwd_corr_launch<0, T, T>(g, out, wbuf, dc1, B, H, W, C, r, gps, ops, st, dev);
+  if (rc) return rc;
+  rc = bwd_corr_launch<1, T, float>(g, out, c1, dwbuf, B, H, W, C, r, gps, ops, st, dev);
+  if (rc) return rc;
+  float* acc = sizeof(T) == 4 ? (float*)dc2 : (float*)(base + L.acc_off);
+  PWC_CUDA(cudaMemsetAsync(acc, 0, n * 4, st));
+  rc = warp_bwd_launch<T, TF, float>(dwbuf, c2, flow, scale, acc, dflow, B, H, W, C, st, dev);
+  if (rc) return rc;
+  if (sizeof(T) != 4) rc = cast_launch<T>(acc, dc2, (int64_t)n, st, dev);
+  return rc;
+}
+
+template <typename T, typename TF>
+int warp_bwd_typed(const void* gout, const void* img, const void* flow, void* dimg, void* dflow, int B, int H, int W,
+                   int C, void* ws, size_t ws_bytes, cudaStream_t st, const DevInfo& dev) {
+  const size_t n = (size_t)B * H * W * C;
+  float* acc = (float*)dimg;
+  if (sizeof(T) != 4) {
+    if (ws == nullptr || ws_bytes < up256(n * 4))
+      return fail(PWC_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", up256(n * 4), ws_bytes);
+    if (!aligned(ws, 256)) return fail(PWC_ERR_ALIGN, "workspace must be 256-byte aligned");
+    acc = (float*)ws;
+  }
+  PWC_CUDA(cudaMemsetAsync(acc, 0, n * 4, st));
+  int rc = warp_bwd_launch<T, TF, T>(gout, img, flow, 1.0f, acc, dflow, B, H, W, C, st, dev);
+  if (rc) return rc;
+  if (sizeof(T) != 4) rc = cast_launch<T>(acc, dimg, (int64_t)n, st, dev);
+  return rc;
+}
+
+}  // namespace
+
+// =========================================================================================
+extern "C" {
+
+int pwc_abi_version(void) { return PWC_ABI_VERSION; }
+const char* pwc_last_error(void) { return g_err.c_str(); }
+uint64_t pwc_launch_count(void) { return g_launches.load(); }
+
+int pwc_set_option(const char* key, int value) {
+  if (!key) return fail(PWC_ERR_BAD_ARG, "null option key");
+  if (!strcmp(key, "fwd_impl")) {
+    if (value < 0 || value > 3) return fail(PWC_ERR_BAD_ARG, "fwd_impl must be 0..3");
+    g_fwd_impl.store(value);
+    return PWC_OK;
+  }
+  if (!strcmp(key, "stream_ctas")) {
+    g_stream_ctas.store(value);
+    return PWC_OK;
+  }
+  return fail(PWC_ERR_BAD_ARG, "unknown option '%s'", key);
+}
+int pwc_get_option(const char* key, int* value) {
+  if (!key || !value) return fail(PWC_ERR_BAD_ARG, "null argument");
+  if (!strcmp(key, "fwd_impl")) { *value = g_fwd_impl.load(); return PWC_OK; }
+  if (!strcmp(key, "stream_ctas")) { *value = g_stream_ctas.load(); return PWC_OK; }
+  return fail(PWC_ERR_BAD_ARG, "unknown option '%s'", key);
+}
+
+int pwc_cost_volume_fwd(const void* c1, const void* warp, void* out, int B, int H, int W, int C, int r, int dtype,
+                        int64_t out_pixel_stride, void* cuda_stream) {
+  return fwd_entry(c1, warp, nullptr, 1.0f, out, B, H, W, C, r, dtype, dtype, out_pixel_stride, cuda_stream);
+}
+
+int pwc_dense_image_warp_fwd(const void* image, const void* flow, void* out, int B, int H, int W, int C, int img_dtype,
+                             int flow_dtype, void* cuda_stream) {
+  return warp_fwd_entry(image, flow, 1.0f, out, B, H, W, C, img_dtype, flow_dtype, (cudaStream_t)cuda_stream);
+}
+
+int pwc_warp_cost_volume_fwd(const void* c1, const void* c2, const void* flow, float flow_scale, void* out, int B,
+                             int H, int W, int C, int r, int dtype, int flow_dtype, int64_t out_pixel_stride,
+                             void* cuda_stream) {
+  return fwd_entry(c1, c2, flow, flow_scale, out, B, H, W, C, r, dtype, flow_dtype, out_pixel_stride, cuda_stream);
+}
+
+int pwc_pyramid_fwd(const pwc_level_t* levels, int n_levels, int B, int r, int dtype, int flow_dtype,
+                    void* cuda_stream) {
+  if (n_levels < 0 || (n_levels > 0 && !levels)) return fail(PWC_ERR_BAD_ARG, "bad level list");
+  for (int i = 0; i < n_levels; ++i) {
+    const pwc_level_t& L = levels[i];
+    int rc = fwd_entry(L.c1, L.c2, L.flow, L.flow_scale, L.out, B, L.H, L.W, L.C, r, dtype, flow_dtype,
+                       L.out_pixel_stride, cuda_stream);
+    if (rc) return rc;
+  }
+  return PWC_OK;
+}
+
+// ---- host-buffer path --------------------------------------------------------------------
+struct pwc_host_ctx {
+  cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+  std::vector<cudaEvent_t> ev_in, ev_run;
+  struct Buf { void* p = nullptr; size_t n = 0; };
+  std::vector<Buf> bufs;  // 4 per level: c1, c2, flow, out
+};
+
+int pwc_host_ctx_create(pwc_host_ctx** ctx) {
+  if (!ctx) return fail(PWC_ERR_BAD_ARG, "null ctx pointer");
+  DevInfo dev;
+  int rc = device_info(&dev);
+  if (rc) return rc;
+  pwc_host_ctx* c = new (std::nothrow) pwc_host_ctx();
+  if (!c) return fail(PWC_ERR_BAD_ARG, "out of host memory");
+  PWC_CUDA(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+  PWC_CUDA(cudaStreamCreateWithFlags(&c->s_run, cudaStreamNonBlocking));
+  PWC_CUDA(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+  *ctx = c;
+  return PWC_OK;
+}
+
+int pwc_host_ctx_destroy(pwc_host_ctx* c) {
+  if (!c) return PWC_OK;
+  for (auto& b : c->bufs)
+    if (b.p) cudaFree(b.p);
+  for (auto e : c->ev_in) cudaEventDestroy(e);
+  for (auto e : c->ev_run) cudaEventDestroy(e);
+  if (c->s_in) cudaStreamDestroy(c->s_in);
+  if (c->s_run) cudaStreamDestroy(c->s_run);
+  if (c->s_out) cudaStreamDestroy(c->s_out);
+  delete c;
+  return PWC_OK;
+}
+
+static int ctx_reserve(pwc_host_ctx* c, size_t slot, size_t bytes) {
+  if (c->bufs.size() <= slot) c->bufs.resize(slot + 1);
+  auto& b = c->bufs[slot];
+  if (b.n < bytes) {
+    if (b.p) PWC_CUDA(cudaFree(b.p));
+    b.p = nullptr;
+    b.n = 0;
+    PWC_CUDA(cudaMalloc(&b.p, bytes));
+    b.n = bytes;
+  }
+  return PWC_OK;
+}
+
+int pwc_pyramid_fwd_host(pwc_host_ctx* c, const pwc_level_t* lv, int n_levels, int B, int r, int dtype,
+                         int flow_dtype) {
+  if (!c || n_levels < 0 || (n_levels > 0 && !lv)) return fail(PWC_ERR_BAD_ARG, "bad arguments");
+  if (!dtype_ok(dtype) || !dtype_ok(flow_dtype)) return fail(PWC_ERR_BAD_DTYPE, "unknown dtype");
+  const size_t es = elt_size(dtype), fs = elt_size(flow_dtype);
+  const int64_t D = (int64_t)(2 * r + 1) * (2 * r + 1);
+  while ((int)c->ev_in.size() < n_levels) {
+    cudaEvent_t e1, e2;
+    PWC_CUDA(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+    PWC_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+    c->ev_in.push_back(e1);
+    c->ev_run.push_back(e2);
+  }
+  // largest level first so the copy engines and the SMs overlap for longest
+  for (int i = 0; i < n_levels; ++i) {
+    const pwc_level_t& L = lv[i];
+    int rc = check_shape(B, L.H, L.W, L.C, r, L.flow != nullptr);
+    if (rc) return rc;
+    const size_t npix = (size_t)B * L.H * L.W;
+    const int64_t ops = L.out_pixel_stride ? L.out_pixel_stride : D;
+    const size_t nb_feat = npix * L.C * es, nb_flow = npix * 2 * fs, nb_out = npix * ops * es;
+    if ((rc = ctx_reserve(c, 4 * i + 0, nb_feat))) return rc;
+    if ((rc = ctx_reserve(c, 4 * i + 1, nb_feat))) return rc;
+    if (L.flow && (rc = ctx_reserve(c, 4 * i + 2, nb_flow))) return rc;
+    if ((rc = ctx_reserve(c, 4 * i + 3, nb_out))) return rc;
+    void* d_c1 = c->bufs[4 * i + 0].p;
+    void* d_c2 = c->bufs[4 * i + 1].p;
+    void* d_fl = L.flow ? c->bufs[4 * i + 2].p : nullptr;
+    void* d_out = c->bufs[4 * i + 3].p;
+    if (npix == 0) continue;
+    PWC_CUDA(cudaMemcpyAsync(d_c1, L.c1, nb_feat, cudaMemcpyHostToDevice, c->s_in));
+    PWC_CUDA(cudaMemcpyAsync(d_c2, L.c2, nb_feat, cudaMemcpyHostToDevice, c->s_in));
+    if (L.flow) PWC_CUDA(cudaMemcpyAsync(d_fl, L.flow, nb_flow, cudaMemcpyHostToDevice, c->s_in));
+    PWC_CUDA(cudaEventRecord(c->ev_in[i], c->s_in));
+    PWC_CUDA(cudaStreamWaitEvent(c->s_run, c->ev_in[i], 0));
+    rc = fwd_entry(d_c1, d_c2, d_fl, L.flow_scale, d_out, B, L.H, L.W, L.C, r, dtype, flow_dtype, ops, c->s_run);
+    if (rc) return rc;
+    PWC_CUDA(cudaEventRecord(c->ev_run[i], c->s_run));
+    PWC_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_run[i], 0));
+    PWC_CUDA(cudaMemcpyAsync(L.out, d_out, nb_out, cudaMemcpyDeviceToHost, c->s_out));
+  }
+  PWC_CUDA(cudaStreamSynchronize(c->s_out));
+  PWC_CUDA(cudaStreamSynchronize(c->s_in));
+  return PWC_OK;
+}
+
+// ---- backward ------------------------------------------------------------------------------
+size_t pwc_bwd_workspace_bytes(int B, int H, int W, int C, int r, int dtype, int has_flow) {
+  (void)r;
+  if (B < 0 || H < 0 || W < 0 || C < 0) return 0;
+  // covers both the fused backward and the standalone warp backward (which needs only the fp32 accumulator)
+  return bwd_ws_layout(B, H, W, C, dtype, has_flow != 0).total;
+}
+
+int pwc_cost_volume_bwd(const void* g, const void* out, const void* c1, const void* warp, void* dc1, void* dwarp, int B,
+                        int H, int W, int C, int r, int dtype, int64_t gps, int64_t ops, void* cuda_stream) {
+  if (!dtype_ok(dtype)) return fail(PWC_ERR_BAD_DTYPE, "unknown dtype");
+  int rc = check_shape(B, H, W, C, r, false);
+  if (rc) return rc;
+  if ((int64_t)B * H * W == 0) return PWC_OK;
+  if (!g || !out || !c1 || !warp || !dc1 || !dwarp) return fail(PWC_ERR_BAD_ARG, "null tensor pointer");
+  const int64_t D = (int64_t)(2 * r + 1) * (2 * r + 1);
+  if (gps == 0) gps = D;
+  if (ops == 0) ops = D;
+  DevInfo dev;
+  rc = device_info(&dev);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if (dtype == PWC_F32) return cv_bwd_typed<float>(g, out, c1, warp, dc1, dwarp, B, H, W, C, r, gps, ops, st, dev);
+  if (dtype == PWC_F16) return cv_bwd_typed<__half>(g, out, c1, warp, dc1, dwarp, B, H, W, C, r, gps, ops, st, dev);
+  return cv_bwd_typed<__nv_bfloat16>(g, out, c1, warp, dc1, dwarp, B, H, W, C, r, gps, ops, st, dev);
+}
+
+int pwc_dense_image_warp_bwd(const void* gout, const void* image, const void* flow, void* dimage, void* dflow, int B,
+                             int H, int W, int C, int img_dtype, int flow_dtype, void* workspace,
+                             size_t workspace_bytes, void* cuda_stream) {
+  if (!dtype_ok(img_dtype) || !dtype_ok(flow_dtype)) return fail(PWC_ERR_BAD_DTYPE, "unknown dtype");
+  int rc = check_shape(B, H, W, C, 0, true);
+  if (rc) return rc;
+  if ((int64_t)B * H * W == 0) return PWC_OK;
+  if (!gout || !image || !flow || !dimage || !dflow) return fail(PWC_ERR_BAD_ARG, "null tensor pointer");
+  DevInfo dev;
+  rc = device_info(&dev);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+#define PWC_WB(T, TF) return warp_bwd_typed<T, TF>(gout, image, flow, dimage, dflow, B, H, W, C, workspace, workspace_bytes, st, dev)
+  if (img_dtype == PWC_F32 && flow_dtype == PWC_F32) PWC_WB(float, float);
+  if (img_dtype == PWC_F16 && flow_dtype == PWC_F16) PWC_WB(__half, __half);
+  if (img_dtype == PWC_F16 && flow_dtype == PWC_F32) PWC_WB(__half, float);
+  if (img_dtype == PWC_BF16 && flow_dtype == PWC_BF16) PWC_WB(__nv_bfloat16, __nv_bfloat16);
+  if (img_dtype == PWC_BF16 && flow_dtype == PWC_F32) PWC_WB(__nv_bfloat16, float);
+#undef PWC_WB
+  return fail(PWC_ERR_BAD_DTYPE, "unsupported (image dtype %d, flow dtype %d) combination", img_dtype, flow_dtype);
+}
+
+int pwc_warp_cost_volume_bwd(const void* g, const void* out, const void* c1, const void* c2, const void* flow,
+                             float flow_scale, void* dc1, void* dc2, void* dflow, int B, int H, int W, int C, int r,
+                             int dtype, int flow_dtype, int64_t gps, int64_t ops, void* workspace,
+                             size_t workspace_bytes, void* cuda_stream) {
+  if (!dtype_ok(dtype) || (flow && !dtype_ok(flow_dtype))) return fail(PWC_ERR_BAD_DTYPE, "unknown dtype");
+  int rc = check_shape(B, H, W, C, r, flow != nullptr);
+  if (rc) return rc;
+  if ((int64_t)B * H * W == 0) return PWC_OK;
+  if (!g || !out || !c1 || !c2 || !dc1 || !dc2 || (flow && !dflow)) return fail(PWC_ERR_BAD_ARG, "null tensor pointer");
+  const int64_t D = (int64_t)(2 * r + 1) * (2 * r + 1);
+  if (gps == 0) gps = D;
+  if (ops == 0) ops = D;
+  DevInfo dev;
+  rc = device_info(&dev);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if (!flow) flow_dtype = dtype;
+#define PWC_FB(T, TF)                                                                                              \
+  return fused_bwd_typed<T, TF>(g, out, c1, c2, flow, flow_scale, dc1, dc2, dflow, B, H, W, C, r, dtype, gps, ops, \
+                                workspace, workspace_bytes, st, dev)
+  if (dtype == PWC_F32 && flow_dtype == PWC_F32) PWC_FB(float, float);
+  if (dtype == PWC_F16 && flow_dtype == PWC_F16) PWC_FB(__half, __half);
+  if (dtype == PWC_F16 && flow_dtype == PWC_F32) PWC_FB(__half, float);
+  if (dtype == PWC_BF16 && flow_dtype == PWC_BF16) PWC_FB(__nv_bfloat16, __nv_bfloat16);
+  if (dtype == PWC_BF16 && flow_dtype == PWC_F32) PWC_FB(__nv_bfloat16, float);
+#undef PWC_FB
+  return fail(PWC_ERR_BAD_DTYPE, "unsupported (feature dtype %d, flow dtype %d) combination", dtype, flow_dtype);
+}
+
+}  // extern "C"
