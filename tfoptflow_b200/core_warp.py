@@ -47,6 +47,10 @@ class WarpedTensor:
     def __getattr__(self, item):  # only reached for names not defined above
         return getattr(self.materialize(), item)
 
+    def __repr__(self):
+        state = "materialised" if self._value is not None else "lazy"
+        return f"WarpedTensor({self.name}, shape={list(self.shape)}, dtype={self.dtype}, {state})"
+
     @classmethod
     def __torch_function__(cls, func, types, args=(), kwargs=None):
         def unwrap(x):
@@ -56,6 +60,19 @@ class WarpedTensor:
                 return type(x)(unwrap(y) for y in x)
             return x
         return func(*unwrap(args), **{k: unwrap(v) for k, v in (kwargs or {}).items()})
+
+
+def _forward_op(name):
+    def op(self, *args, **kwargs):
+        return getattr(self.materialize(), name)(*args, **kwargs)
+    op.__name__ = name
+    return op
+
+
+for _n in ("add", "radd", "sub", "rsub", "mul", "rmul", "truediv", "rtruediv", "neg", "pow", "matmul", "getitem",
+           "eq", "ne", "lt", "le", "gt", "ge", "abs", "len", "iter", "float", "bool"):
+    setattr(WarpedTensor, f"__{_n}__", _forward_op(f"__{_n}__"))
+WarpedTensor.__hash__ = object.__hash__  # defining __eq__ would otherwise drop it
 
 
 def dense_image_warp(image, flow, name="dense_image_warp", lazy: bool = True):

@@ -1,0 +1,422 @@
+// Streaming fused warp + cost-volume forward (v2) for search_range 4 and C in {16, 32}.
+//
+// Persistent, warp-specialised kernel, one CTA per SM.  The image is cut into vertical strips of
+// TW = 32 pixels; every CTA owns a contiguous range of (strip, row-pair) work and marches down it.
+//   * 4 producer warps evaluate the bilinear warp of c2 (whole 128-byte pixel vectors per corner, so
+//     every gather touches full cache lines) and stream the *warped* rows, plus the matching c1 rows,
+//     into two shared-memory rings guarded by mbarriers.  Warped features never reach HBM.
+//   * 4 compute warps pull tasks in order.  A full task F(m) takes one "slab" (warped rows 2m-1, 2m)
+//     against the 4 row pairs that can see it; each lane owns a register tile of 2 rows x 8 pixels x
+//     9 dx (144 accumulators) for one (pair, B row): row 2k uses dy = D, row 2k+1 uses dy = D-1 with
+//     the SAME warped row, so every shared-memory operand feeds 18 FMAs per LDS.128.  Lanes of a warp
+//     are arranged (pair, B row, x-group) so that c1 operands are shared by the two B rows and warped
+//     operands by the four pairs (broadcast within the LDS wavefront).
+//     The two displacements the 8-row window cannot reach (row 2m+4 with dy=-4, row 2m-5 with dy=+4)
+//     are done by an edge task E(g) per group of 4 slabs (72 accumulators per lane).
+//   * Results go through a per-warp transposition buffer so global stores are runs of 18 (9)
+//     contiguous floats.
+// Zero padding is applied after warping (core_costvol.py:27); the warp clamps (core_warp.py:101-104).
+#pragma once
+#include "common.cuh"
+
+namespace pwc {
+namespace stream {
+
+constexpr int R = 4, ND = 9, D = 81;
+constexpr int PX = 8, NXG = 4, TW = PX * NXG;  // 32-pixel strips
+constexpr int NCW = 4;                          // compute warps
+constexpr int NPW = 4;                          // producer warps
+constexpr int NTHREADS = 32 * (NCW + NPW);
+constexpr int NPROD = 32 * NPW;
+constexpr int BU = TW + 2 * R;                  // 40 warped pixels per row
+constexpr int B_USLOTS = BU + BU / PX - 1;      // 44 (slot(u) = u + u/8)
+constexpr int A_ROWSLOTS = TW + TW / PX;        // 36
+constexpr int MAXSEG = 8;
+
+template <int KV>
+struct Geo {
+  static constexpr int B_PLANE = B_USLOTS * 2 + 1;      // 89 float4, odd => kv-strided stores conflict-free
+  static constexpr int A_PLANE = A_ROWSLOTS * 2 + 1;    // 73
+  static constexpr int BSLOT = KV * B_PLANE;            // float4 per slab slot
+  static constexpr int ASLOT = KV * A_PLANE;            // float4 per pair slot
+  static constexpr int NSLAB = KV == 8 ? 8 : 12;        // ring depths
+  static constexpr int NAP = KV == 8 ? 13 : 18;
+  static constexpr int STAGE_WORDS = 320;               // per compute warp
+  static constexpr size_t OFF_B = 0;
+  static constexpr size_t OFF_A = OFF_B + (size_t)NSLAB * BSLOT * 16;
+  static constexpr size_t OFF_STAGE = OFF_A + (size_t)NAP * ASLOT * 16;
+  static constexpr size_t OFF_BAR = OFF_STAGE + (size_t)NCW * STAGE_WORDS * 4;
+  static constexpr size_t OFF_SEG = OFF_BAR + (size_t)(2 * NSLAB + 2 * NAP) * 8;
+  static constexpr size_t SMEM_BYTES = OFF_SEG + MAXSEG * 32 + 64;
+};
+
+struct Seg {
+  int b, x0, p0, p1;   // batch, strip origin, pair range [p0, p1)
+  int nslab;           // p1 - p0 + 5 slabs: m = p0-2 .. p1+2
+  int task0, j0, a0;   // first global task / slab / pair index of this segment
+};
+
+struct Params {
+  int B, H, W, C;
+  int64_t ops;      // out pixel stride (elements)
+  float flow_scale;
+  int NPAIR;        // ceil(H / 2)
+  int nstrip_x;     // ceil(W / TW)
+  long long Q;      // total (strip, pair) units
+};
+
+// ---- mbarrier helpers (generic-proxy producers/consumers only) ---------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+// ---- producer ------------------------------------------------------------------------------
+template <int KV, typename T, typename TF>
+__device__ __forceinline__ void produce_pair(const T* __restrict__ c1, const Params& P, const Seg& sg, int k,
+                                             float4* __restrict__ sA_slot, int ptid) {
+  // rows 2k, 2k+1 of the strip: 2 x 32 pixels x KV vectors
+  constexpr int ITEMS = 2 * TW * KV;
+#pragma unroll
+  for (int it = 0; it < ITEMS / NPROD; ++it) {
+    const int id = it * NPROD + ptid;
+    const int kv = id % KV, pxl = id / KV;
+    const int row = pxl / TW, col = pxl - row * TW;
+    const int y = 2 * k + row, x = sg.x0 + col;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (y < P.H && x < P.W) v = ld4(c1 + (((size_t)sg.b * P.H + y) * P.W + x) * P.C + 4 * kv);
+    sA_slot[kv * Geo<KV>::A_PLANE + row * A_ROWSLOTS + col + col / PX] = v;
+  }
+}
+
+template <int KV, typename T, typename TF>
+__device__ __forceinline__ void produce_slab(const T* __restrict__ c2, const TF* __restrict__ flow, const Params& P,
+                                             const Seg& sg, int m, float4* __restrict__ sB_slot, int pwarp, int lane) {
+  // warped rows 2m-1 (bsel 0) and 2m (bsel 1), u = 0..39 <-> x = x0 - 4 + u : 80 pixels, 20 per producer warp
+  constexpr int PPW = 2 * BU / NPW;   // 20 pixels per warp
+  constexpr int LPP = KV;             // lanes per pixel
+  constexpr int PPI = 32 / LPP;       // pixels per iteration
+  constexpr int NIT = (PPW + PPI - 1) / PPI;
+  // phase 1: lanes 0..19 compute the sampling coordinates of "their" pixel
+  int c_pix = 0, c_flag = 0;
+  float c_ax = 0.f, c_ay = 0.f;
+  if (lane < PPW) {
+    const int e = pwarp * PPW + lane;
+    const int bsel = e / BU, u = e - bsel * BU;
+    const int y = 2 * m - 1 + bsel, x = sg.x0 - R + u;
+    if (y >= 0 && y < P.H && x >= 0 && x < P.W) {
+      if (flow != nullptr) {
+        const SampleCoord s = sample_coord<T, TF>(flow, P.flow_scale, sg.b, y, x, P.H, P.W);
+        c_pix = s.pix; c_ax = s.ax; c_ay = s.ay; c_flag = 1;
+      } else {
+        c_pix = (sg.b * P.H + y) * P.W + x; c_flag = 2;
+      }
+    }
+  }
+  // phase 2: LPP lanes per pixel gather the 4 corners (full pixel vectors) and lerp
+  const int kv = lane % LPP, sub = lane / LPP;
+  float4 tl[NIT], tr[NIT], bl[NIT], br[NIT];
+  int flag[NIT];
+  float ax[NIT], ay[NIT];
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int pl = it * PPI + sub;  // local pixel
+    const int src = pl < PPW ? pl : 0;
+    const int pix = __shfl_sync(0xffffffffu, c_pix, src);
+    ax[it] = __shfl_sync(0xffffffffu, c_ax, src);
+    ay[it] = __shfl_sync(0xffffffffu, c_ay, src);
+    const int fl = __shfl_sync(0xffffffffu, c_flag, src);
+    flag[it] = pl < PPW ? fl : -1;
+    tl[it] = tr[it] = bl[it] = br[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (flag[it] > 0) {
+      const T* base = c2 + (size_t)pix * P.C + 4 * kv;
+      tl[it] = ld4(base);
+      if (flag[it] == 1) {
+        tr[it] = ld4(base + P.C);
+        bl[it] = ld4(base + (size_t)P.W * P.C);
+        br[it] = ld4(base + (size_t)P.W * P.C + P.C);
+      }
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    if (flag[it] < 0) continue;
+    float4 v = tl[it];
+    if (flag[it] == 1) v = round4<T>(bilerp4(tl[it], tr[it], bl[it], br[it], ax[it], ay[it]));
+    const int e = pwarp * PPW + it * PPI + sub;
+    const int bsel = e / BU, u = e - bsel * BU;
+    sB_slot[kv * Geo<KV>::B_PLANE + (u + u / PX) * 2 + bsel] = v;
+  }
+}
+
+// ---- per-lane correlation: NSUB rows x 8 pixels x 9 dx against ONE warped row ---------------
+template <int KV, int NSUB>
+__device__ __forceinline__ void correlate(const float4* __restrict__ a0p, const float4* __restrict__ a1p,
+                                          const float4* __restrict__ bp, float (&acc)[NSUB][PX][ND]) {
+#pragma unroll 2
+  for (int kv = 0; kv < KV; ++kv) {
+    // pixel-major order: the warped window slides (9 live float4), c1 operands live for one pixel only
+    float4 bw[PX + 2 * R];
+#pragma unroll
+    for (int k = 0; k < ND; ++k) bw[k] = bp[kv * Geo<KV>::B_PLANE + (k + k / PX) * 2];
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+      if (p > 0) bw[p + ND - 1] = bp[kv * Geo<KV>::B_PLANE + ((p + ND - 1) + (p + ND - 1) / PX) * 2];
+      const float4 a0 = a0p[kv * Geo<KV>::A_PLANE + p];
+      float4 a1 = a0;
+      if (NSUB == 2) a1 = a1p[kv * Geo<KV>::A_PLANE + p];
+#pragma unroll
+      for (int d = 0; d < ND; ++d) {
+        fma4(acc[0][p][d], a0, bw[p + d]);
+        if (NSUB == 2) fma4(acc[NSUB - 1][p][d], a1, bw[p + d]);
+      }
+    }
+  }
+}
+
+template <int KV, typename T, typename TF>
+__global__ void __launch_bounds__(NTHREADS, 1)
+fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* __restrict__ flow,
+                  T* __restrict__ out, const Params P) {
+  using G = Geo<KV>;
+  extern __shared__ __align__(16) unsigned char smem[];
+  float4* sB = reinterpret_cast<float4*>(smem + G::OFF_B);
+  float4* sA = reinterpret_cast<float4*>(smem + G::OFF_A);
+  float* sStage = reinterpret_cast<float*>(smem + G::OFF_STAGE);
+  uint64_t* fullB = reinterpret_cast<uint64_t*>(smem + G::OFF_BAR);
+  uint64_t* emptyB = fullB + G::NSLAB;
+  uint64_t* fullA = emptyB + G::NSLAB;
+  uint64_t* emptyA = fullA + G::NAP;
+  Seg* segs = reinterpret_cast<Seg*>(smem + G::OFF_SEG);
+  int* s_misc = reinterpret_cast<int*>(smem + G::OFF_SEG + MAXSEG * 32);  // [0] nseg, [1] total tasks, [2] task counter
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i < G::NSLAB; ++i) { mbar_init(&fullB[i], NPROD); mbar_init(&emptyB[i], 2); }
+    for (int i = 0; i < G::NAP; ++i) { mbar_init(&fullA[i], NPROD); mbar_init(&emptyA[i], 6); }
+    // this CTA's contiguous range of (strip, pair) units, cut into per-strip segments
+    const long long qlo = P.Q * blockIdx.x / gridDim.x, qhi = P.Q * (blockIdx.x + 1) / gridDim.x;
+    int n = 0, task = 0, j = 0, a = 0;
+    long long q = qlo;
+    while (q < qhi && n < MAXSEG) {
+      const long long strip = q / P.NPAIR;
+      const int p0 = (int)(q - strip * P.NPAIR);
+      const long long rem = qhi - q;
+      const int p1 = (int)((long long)(P.NPAIR - p0) < rem ? P.NPAIR : p0 + rem);
+      Seg s;
+      s.b = (int)(strip / P.nstrip_x);
+      s.x0 = (int)(strip % P.nstrip_x) * TW;
+      s.p0 = p0; s.p1 = p1; s.nslab = p1 - p0 + 5;
+      s.task0 = task; s.j0 = j; s.a0 = a;
+      task += 5 * ((s.nslab + 3) / 4);
+      j += s.nslab;
+      a += p1 - p0;
+      segs[n++] = s;
+      q += p1 - p0;
+    }
+    s_misc[0] = n; s_misc[1] = task; s_misc[2] = 0;
+  }
+  __syncthreads();
+  const int nseg = s_misc[0];
+
+  if (warp >= NCW) {
+    // =========================== producers ===========================
+    const int pwarp = warp - NCW, ptid = tid - 32 * NCW;
+    for (int si = 0; si < nseg; ++si) {
+      const Seg sg = segs[si];
+      for (int l = 0; l < sg.nslab; ++l) {
+        if (sg.p0 + l < sg.p1) {
+          const int ag = sg.a0 + l, slot = ag % G::NAP, use = ag / G::NAP;
+          mbar_wait(&emptyA[slot], (use & 1) ^ 1);
+          produce_pair<KV, T, TF>(c1, P, sg, sg.p0 + l, sA + (size_t)slot * G::ASLOT, ptid);
+          mbar_arrive(&fullA[slot]);
+        }
+        const int jg = sg.j0 + l, slot = jg % G::NSLAB, use = jg / G::NSLAB;
+        const int m = sg.p0 - 2 + l;
+        mbar_wait(&emptyB[slot], (use & 1) ^ 1);
+        if (2 * m >= 0 && 2 * m - 1 < P.H)  // slabs entirely outside the image are never read
+          produce_slab<KV, T, TF>(c2, flow, P, sg, m, sB + (size_t)slot * G::BSLOT, pwarp, lane);
+        mbar_arrive(&fullB[slot]);
+      }
+    }
+    return;
+  }
+
+  // =========================== compute warps ===========================
+  float* stage = sStage + warp * G::STAGE_WORDS;
+  const float inv_c = 1.0f / (float)P.C;
+  const int total_tasks = s_misc[1];
+  const int xg = lane & 3;
+  while (true) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(&s_misc[2], 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= total_tasks) break;
+    int si = 0;
+    while (si + 1 < nseg && segs[si + 1].task0 <= t) ++si;
+    const Seg sg = segs[si];
+    const int tl = t - sg.task0, g = tl / 5, rr = tl - 5 * g;
+
+    if (rr < 4) {
+      // ------------------------- full task F(l) -------------------------
+      const int l = 4 * g + rr;
+      if (l >= sg.nslab) continue;
+      const int m = sg.p0 - 2 + l;
+      const int bsel = (lane >> 2) & 1, pk = lane >> 3;
+      const int k = m - 2 + pk;
+      const bool pair_ok = (k >= sg.p0) && (k < sg.p1);
+      const int jg = sg.j0 + l, sb = jg % G::NSLAB;
+      const int ag = sg.a0 + (pair_ok ? k - sg.p0 : 0), sa = ag % G::NAP;
+      mbar_wait(&fullB[sb], (jg / G::NSLAB) & 1);
+      if (pair_ok) mbar_wait(&fullA[sa], (ag / G::NAP) & 1);
+      const int yb = 2 * m - 1 + bsel;
+      const bool active = pair_ok && yb >= 0 && yb < P.H;
+
+      float acc[2][PX][ND];
+#pragma unroll
+      for (int s = 0; s < 2; ++s)
+#pragma unroll
+        for (int p = 0; p < PX; ++p)
+#pragma unroll
+          for (int d = 0; d < ND; ++d) acc[s][p][d] = 0.f;
+      if (active) {
+        const float4* ap = sA + (size_t)sa * G::ASLOT + xg * (PX + 1);
+        const float4* bp = sB + (size_t)sb * G::BSLOT + xg * (PX + 1) * 2 + bsel;
+        correlate<KV, 2>(ap, ap + A_ROWSLOTS, bp, acc);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&emptyB[sb]);
+      if (pair_ok && (lane & 7) == 0) mbar_arrive(&emptyA[sa]);
+
+      // epilogue: per (row s, pixel p) the warp holds 16 runs of 18 contiguous channels
+      const int D0 = 3 - 2 * pk;  // dy of row 2k for bsel = 0
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+          const int grp = pk * 4 + xg;
+#pragma unroll
+          for (int d = 0; d < ND; ++d) stage[grp * 19 + bsel * 9 + d] = lrelu01(acc[s][p][d] * inv_c);
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 9; ++it) {
+            const int idx = it * 32 + lane;
+            const int g2 = idx / 18, w = idx - g2 * 18;
+            const int pk2 = g2 >> 2, xg2 = g2 & 3;
+            const int k2 = m - 2 + pk2;
+            const int y = 2 * k2 + s, x = sg.x0 + xg2 * PX + p;
+            if (k2 >= sg.p0 && k2 < sg.p1 && y < P.H && x < P.W) {
+              const int ch = (7 - 2 * pk2 - s) * ND + w;
+              out[(((size_t)sg.b * P.H + y) * P.W + x) * P.ops + ch] = ElemTraits<T>::from_f(stage[g2 * 19 + w]);
+            }
+          }
+          __syncwarp();
+        }
+      }
+      (void)D0;
+    } else {
+      // ------------------------- edge task E(g): slabs 4g .. 4g+3 -------------------------
+      const int half = (lane >> 2) & 1, ms = lane >> 3;
+      const int l = 4 * g + ms;
+      const bool slab_ok = l < sg.nslab;
+      const int m = sg.p0 - 2 + l;
+      // half 0: row 2m+4 (pair m+2, sub 0) vs warped row 2m   (bsel 1), dy = -4 -> dyi 0
+      // half 1: row 2m-5 (pair m-3, sub 1) vs warped row 2m-1 (bsel 0), dy = +4 -> dyi 8
+      const int k = half == 0 ? m + 2 : m - 3;
+      const int sub = half, bsel = 1 - half;
+      const bool pair_ok = slab_ok && k >= sg.p0 && k < sg.p1;
+      const int jg = sg.j0 + (slab_ok ? l : 0), sb = jg % G::NSLAB;
+      const int ag = sg.a0 + (pair_ok ? k - sg.p0 : 0), sa = ag % G::NAP;
+      if (slab_ok) mbar_wait(&fullB[sb], (jg / G::NSLAB) & 1);
+      if (pair_ok) mbar_wait(&fullA[sa], (ag / G::NAP) & 1);
+      const int yb = 2 * m - 1 + bsel, ya = 2 * k + sub;
+      const bool active = pair_ok && yb >= 0 && yb < P.H && ya < P.H;
+
+      float acc[1][PX][ND];
+#pragma unroll
+      for (int p = 0; p < PX; ++p)
+#pragma unroll
+        for (int d = 0; d < ND; ++d) acc[0][p][d] = 0.f;
+      if (active) {
+        const float4* ap = sA + (size_t)sa * G::ASLOT + sub * A_ROWSLOTS + xg * (PX + 1);
+        const float4* bp = sB + (size_t)sb * G::BSLOT + xg * (PX + 1) * 2 + bsel;
+        correlate<KV, 1>(ap, ap, bp, acc);
+      }
+      __syncwarp();
+      if (slab_ok && (lane & 7) == 0) mbar_arrive(&emptyB[sb]);          // one arrival per slab (half 0, xg 0)
+      if (pair_ok && (lane & 3) == 0) mbar_arrive(&emptyA[sa]);           // one per (slab, half)
+
+#pragma unroll
+      for (int p = 0; p < PX; ++p) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) stage[lane * 9 + d] = lrelu01(acc[0][p][d] * inv_c);
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 9; ++it) {
+          const int idx = it * 32 + lane;
+          const int l2 = idx / 9, w = idx - l2 * 9;  // source lane
+          const int xg2 = l2 & 3, half2 = (l2 >> 2) & 1, ms2 = l2 >> 3;
+          const int sl2 = 4 * g + ms2, m2 = sg.p0 - 2 + sl2;
+          const int k2 = half2 == 0 ? m2 + 2 : m2 - 3;
+          const int y = 2 * k2 + half2, x = sg.x0 + xg2 * PX + p;
+          if (sl2 < sg.nslab && k2 >= sg.p0 && k2 < sg.p1 && y < P.H && x < P.W) {
+            const int ch = (half2 == 0 ? 0 : 8) * ND + w;
+            out[(((size_t)sg.b * P.H + y) * P.W + x) * P.ops + ch] = ElemTraits<T>::from_f(stage[l2 * 9 + w]);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
+// Host-side launcher.  Returns 0 when launched, 1 when the shape is not covered, -1 on a CUDA error.
+template <typename T, typename TF>
+int launch(const T* c1, const T* c2, const TF* flow, float flow_scale, T* out, int B, int H, int W, int C,
+           int64_t ops, cudaStream_t st, int sms, int ctas_override) {
+  if (C != 32 && C != 16) return 1;
+  Params P;
+  P.B = B; P.H = H; P.W = W; P.C = C; P.ops = ops; P.flow_scale = flow_scale;
+  P.NPAIR = (H + 1) / 2;
+  P.nstrip_x = (W + TW - 1) / TW;
+  P.Q = (long long)B * P.nstrip_x * P.NPAIR;
+  if (P.Q <= 0) return 1;
+  long long grid = ctas_override > 0 ? ctas_override : sms;
+  if (grid > P.Q) grid = P.Q;
+  // every CTA must fit its range into MAXSEG per-strip segments
+  const long long per = (P.Q + grid - 1) / grid;
+  if (per / P.NPAIR + 2 > MAXSEG) return 1;
+  cudaError_t e;
+  if (C == 32) {
+    auto k = fwd_stream_kernel<8, T, TF>;
+    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<8>::SMEM_BYTES);
+    if (e != cudaSuccess) return -1;
+    k<<<(unsigned)grid, NTHREADS, Geo<8>::SMEM_BYTES, st>>>(c1, c2, flow, out, P);
+  } else {
+    auto k = fwd_stream_kernel<4, T, TF>;
+    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<4>::SMEM_BYTES);
+    if (e != cudaSuccess) return -1;
+    k<<<(unsigned)grid, NTHREADS, Geo<4>::SMEM_BYTES, st>>>(c1, c2, flow, out, P);
+  }
+  return 0;
+}
+
+}  // namespace stream
+}  // namespace pwc

@@ -103,6 +103,12 @@ class HostPyramid:
         for L, o in zip(levels, outs):
             B, H, W, C = L["c1"].shape
             f = L.get("flow")
+            for name, arr in (("c1", L["c1"]), ("c2", L["c2"]), ("flow", f), ("out", o)):
+                if arr is not None and not (isinstance(arr, np.ndarray) and arr.flags["C_CONTIGUOUS"]):
+                    raise ValueError(f"{name} must be a C-contiguous numpy array (NHWC)")
+            if L["c2"].shape != L["c1"].shape or (f is not None and f.shape != (B, H, W, 2)) or \
+                    o.shape != (B, H, W, (2 * int(search_range) + 1) ** 2) or o.dtype != L["c1"].dtype:
+                raise ValueError("c1/c2/flow/out shapes or dtypes do not match")
             descs.append(dict(c1=L["c1"].ctypes.data, c2=L["c2"].ctypes.data, flow=None if f is None else f.ctypes.data,
                               out=o.ctypes.data, H=H, W=W, C=C, flow_scale=float(L.get("scaler", 1.0)),
                               out_pixel_stride=0))

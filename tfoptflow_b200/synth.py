@@ -30,7 +30,7 @@ def _smooth_field(rng, b, h, w, sigma):
     ax = (xs - x0)[None, None, :, None]
     top = coarse[:, y0][:, :, x0] * (1 - ax) + coarse[:, y0][:, :, x0 + 1] * ax
     bot = coarse[:, y0 + 1][:, :, x0] * (1 - ax) + coarse[:, y0 + 1][:, :, x0 + 1] * ax
-    return ((top * (1 - ay) + bot * ay) * sigma).astype(np.float32)
+    return np.ascontiguousarray(((top * (1 - ay) + bot * ay) * sigma).astype(np.float32))
 
 
 def make_level(b, h, w, c, seed, dtype=np.float32, flow="smooth", sigma=2.0, with_grad=False, search_range=4):
@@ -50,7 +50,7 @@ def make_level(b, h, w, c, seed, dtype=np.float32, flow="smooth", sigma=2.0, wit
         f = None
     else:
         raise ValueError(flow)
-    out["flow"] = None if f is None else f.astype(dtype)
+    out["flow"] = None if f is None else np.ascontiguousarray(f.astype(dtype))
     if with_grad:
         d = (2 * search_range + 1) ** 2
         out["g"] = rng.standard_normal((b, h, w, d)).astype(np.float32).astype(dtype)
@@ -69,7 +69,7 @@ def make_pyramid(b, height, width, dtype=np.float32, levels=(6, 5, 4, 3, 2), flo
                        with_grad=with_grad, search_range=search_range)
         # the op sees up_flow (pre-scaler); sigma is chosen post-scaler, so divide it out
         if d["flow"] is not None:
-            d["flow"] = (d["flow"].astype(np.float32) / FLOW_SCALERS[l]).astype(dtype)
+            d["flow"] = np.ascontiguousarray((d["flow"].astype(np.float32) / FLOW_SCALERS[l]).astype(dtype))
         d["lvl"] = l
         d["scaler"] = FLOW_SCALERS[l] if d["flow"] is not None else 1.0
         out.append(d)
