@@ -41,7 +41,7 @@ struct Geo {
   static constexpr int ASLOT = KV * A_PLANE;            // float4 per pair slot
   static constexpr int NSLAB = KV == 8 ? 8 : 12;        // ring depths
   static constexpr int NAP = KV == 8 ? 13 : 18;
-  static constexpr int STAGE_WORDS = 320;               // per compute warp
+  static constexpr int STAGE_WORDS = 640;               // per compute warp (2 x 320, double buffered)
   static constexpr size_t OFF_B = 0;
   static constexpr size_t OFF_A = OFF_B + (size_t)NSLAB * BSLOT * 16;
   static constexpr size_t OFF_STAGE = OFF_A + (size_t)NAP * ASLOT * 16;
@@ -169,7 +169,7 @@ __device__ __forceinline__ void produce_slab(const T* __restrict__ c2, const TF*
 template <int KV, int NSUB>
 __device__ __forceinline__ void correlate(const float4* __restrict__ a0p, const float4* __restrict__ a1p,
                                           const float4* __restrict__ bp, float (&acc)[NSUB][PX][ND]) {
-#pragma unroll 2
+#pragma unroll 1
   for (int kv = 0; kv < KV; ++kv) {
     // pixel-major order: the warped window slides (9 live float4), c1 operands live for one pixel only
     float4 bw[PX + 2 * R];
@@ -305,32 +305,39 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
       if (lane == 0) mbar_arrive(&emptyB[sb]);
       if (pair_ok && (lane & 7) == 0) mbar_arrive(&emptyA[sa]);
 
-      // epilogue: per (row s, pixel p) the warp holds 16 runs of 18 contiguous channels
-      const int D0 = 3 - 2 * pk;  // dy of row 2k for bsel = 0
+      // epilogue: per (row s, pixel p) the warp holds 16 runs of 18 contiguous channels.  Everything that
+      // does not depend on (s, p) is hoisted: element it*32+lane of the 288-float staging block.
+      size_t off[9];
+      int sidx[9], nvx[9], nvy[9];
+#pragma unroll
+      for (int it = 0; it < 9; ++it) {
+        const int idx = it * 32 + lane;
+        const int g2 = idx / 18, w = idx - g2 * 18;
+        const int pk2 = g2 >> 2, xg2 = g2 & 3;
+        const int k2 = m - 2 + pk2;
+        const bool ok = k2 >= sg.p0 && k2 < sg.p1;
+        const int xb = sg.x0 + xg2 * PX, y0 = 2 * k2;
+        nvx[it] = ok ? P.W - xb : 0;
+        nvy[it] = P.H - y0;
+        off[it] = (((size_t)sg.b * P.H + (ok ? y0 : 0)) * P.W + xb) * P.ops + (7 - 2 * pk2) * ND + w;
+        sidx[it] = g2 * 19 + w;
+      }
+      const int grp19 = (pk * 4 + xg) * 19 + bsel * 9;
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
 #pragma unroll
         for (int p = 0; p < PX; ++p) {
-          const int grp = pk * 4 + xg;
+          float* stg = stage + ((s * PX + p) & 1) * 320;
 #pragma unroll
-          for (int d = 0; d < ND; ++d) stage[grp * 19 + bsel * 9 + d] = lrelu01(acc[s][p][d] * inv_c);
+          for (int d = 0; d < ND; ++d) stg[grp19 + d] = lrelu01(acc[s][p][d] * inv_c);
           __syncwarp();
+          const size_t sp = ((size_t)s * P.W + p) * P.ops - (size_t)(s * ND);
 #pragma unroll
-          for (int it = 0; it < 9; ++it) {
-            const int idx = it * 32 + lane;
-            const int g2 = idx / 18, w = idx - g2 * 18;
-            const int pk2 = g2 >> 2, xg2 = g2 & 3;
-            const int k2 = m - 2 + pk2;
-            const int y = 2 * k2 + s, x = sg.x0 + xg2 * PX + p;
-            if (k2 >= sg.p0 && k2 < sg.p1 && y < P.H && x < P.W) {
-              const int ch = (7 - 2 * pk2 - s) * ND + w;
-              out[(((size_t)sg.b * P.H + y) * P.W + x) * P.ops + ch] = ElemTraits<T>::from_f(stage[g2 * 19 + w]);
-            }
-          }
-          __syncwarp();
+          for (int it = 0; it < 9; ++it)
+            if (p < nvx[it] && s < nvy[it]) out[off[it] + sp] = ElemTraits<T>::from_f(stg[sidx[it]]);
         }
       }
-      (void)D0;
+      __syncwarp();
     } else {
       // ------------------------- edge task E(g): slabs 4g .. 4g+3 -------------------------
       const int half = (lane >> 2) & 1, ms = lane >> 3;
@@ -363,26 +370,32 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
       if (slab_ok && (lane & 7) == 0) mbar_arrive(&emptyB[sb]);          // one arrival per slab (half 0, xg 0)
       if (pair_ok && (lane & 3) == 0) mbar_arrive(&emptyA[sa]);           // one per (slab, half)
 
+      size_t off[9];
+      int nvx[9];
+#pragma unroll
+      for (int it = 0; it < 9; ++it) {
+        const int idx = it * 32 + lane;
+        const int l2 = idx / 9, w = idx - l2 * 9;  // source lane, channel within its run
+        const int xg2 = l2 & 3, half2 = (l2 >> 2) & 1, ms2 = l2 >> 3;
+        const int sl2 = 4 * g + ms2, m2 = sg.p0 - 2 + sl2;
+        const int k2 = half2 == 0 ? m2 + 2 : m2 - 3;
+        const int y = 2 * k2 + half2, xb = sg.x0 + xg2 * PX;
+        const bool ok = sl2 < sg.nslab && k2 >= sg.p0 && k2 < sg.p1 && y < P.H;
+        nvx[it] = ok ? P.W - xb : 0;
+        off[it] = (((size_t)sg.b * P.H + (ok ? y : 0)) * P.W + xb) * P.ops + (half2 == 0 ? 0 : 8) * ND + w;
+      }
 #pragma unroll
       for (int p = 0; p < PX; ++p) {
+        float* stg = stage + (p & 1) * 320;
 #pragma unroll
-        for (int d = 0; d < ND; ++d) stage[lane * 9 + d] = lrelu01(acc[0][p][d] * inv_c);
+        for (int d = 0; d < ND; ++d) stg[lane * 9 + d] = lrelu01(acc[0][p][d] * inv_c);
         __syncwarp();
+        const size_t sp = (size_t)p * P.ops;
 #pragma unroll
-        for (int it = 0; it < 9; ++it) {
-          const int idx = it * 32 + lane;
-          const int l2 = idx / 9, w = idx - l2 * 9;  // source lane
-          const int xg2 = l2 & 3, half2 = (l2 >> 2) & 1, ms2 = l2 >> 3;
-          const int sl2 = 4 * g + ms2, m2 = sg.p0 - 2 + sl2;
-          const int k2 = half2 == 0 ? m2 + 2 : m2 - 3;
-          const int y = 2 * k2 + half2, x = sg.x0 + xg2 * PX + p;
-          if (sl2 < sg.nslab && k2 >= sg.p0 && k2 < sg.p1 && y < P.H && x < P.W) {
-            const int ch = (half2 == 0 ? 0 : 8) * ND + w;
-            out[(((size_t)sg.b * P.H + y) * P.W + x) * P.ops + ch] = ElemTraits<T>::from_f(stage[l2 * 9 + w]);
-          }
-        }
-        __syncwarp();
+        for (int it = 0; it < 9; ++it)
+          if (p < nvx[it]) out[off[it] + sp] = ElemTraits<T>::from_f(stg[it * 32 + lane]);
       }
+      __syncwarp();
     }
   }
 }
