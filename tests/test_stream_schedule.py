@@ -1,12 +1,15 @@
 """CPU model of the streaming kernel's work decomposition (tfoptflow_b200/csrc/fwd_stream.cuh): segments,
 slab / pair rings, full tasks F and edge tasks E.  Checks that every (pixel, dy) of the cost volume is produced
 exactly once from the right (c1 row, warped row) combination and that every ring slot gets exactly the number of
-consumer arrivals its mbarrier was initialised with (2 per slab, 6 per pair)."""
+consumer arrivals its mbarrier was initialised with (3 per slab, 6 per pair)."""
 import collections
 
 import pytest
 
 TW, PX = 32, 8
+
+
+TPG = 9  # tasks per group of 4 slabs: Fa, Fb per slab + one edge task
 
 
 def segments(B, H, W, grid, cta):
@@ -20,7 +23,7 @@ def segments(B, H, W, grid, cta):
         rem = qhi - q
         p1 = NPAIR if NPAIR - p0 < rem else p0 + rem
         s = dict(b=strip // nsx, x0=(strip % nsx) * TW, p0=p0, p1=p1, nslab=p1 - p0 + 5, task0=task, j0=j, a0=a)
-        task += 5 * ((s["nslab"] + 3) // 4)
+        task += TPG * ((s["nslab"] + 3) // 4)
         j += s["nslab"]
         a += p1 - p0
         segs.append(s)
@@ -33,49 +36,41 @@ def run_cta(B, H, W, grid, cta, written, slab_arr, pair_arr):
     for t in range(total):
         sg = [s for s in segs if s["task0"] <= t][-1]
         tl = t - sg["task0"]
-        g, rr = divmod(tl, 5)
-        if rr < 4:
-            l = 4 * g + rr
-            if l >= sg["nslab"]:
-                continue
-            m = sg["p0"] - 2 + l
-            slab_arr[(cta, sg["j0"] + l)] += 1
-            for lane in range(32):
-                xg, bsel, pk = lane & 3, (lane >> 2) & 1, lane >> 3
-                k = m - 2 + pk
-                if not (sg["p0"] <= k < sg["p1"]):
-                    continue
-                if lane & 7 == 0:
-                    pair_arr[(cta, sg["a0"] + k - sg["p0"])] += 1
-                yb = 2 * m - 1 + bsel
-                for s in range(2):
-                    ya = 2 * k + s
-                    dyi = 7 - 2 * pk - s + bsel
-                    assert yb - ya == dyi - 4
-                    for p in range(PX):
-                        x = sg["x0"] + xg * PX + p
-                        if ya < H and x < W:
-                            written[(sg["b"], ya, x, dyi)] += 1
-        else:
-            for lane in range(32):
-                xg, half, ms = lane & 3, (lane >> 2) & 1, lane >> 3
-                l = 4 * g + ms
+        g, rr = divmod(tl, TPG)
+        for lane in range(32):
+            xg, lo, hi = (lane >> 1) & 3, lane & 1, lane >> 3
+            if rr < 8:
+                l = 4 * g + (rr >> 1)
+                k = sg["p0"] - 2 + l - 2 + 2 * (rr & 1) + (hi >> 1)
+                sub, bsel = hi & 1, lo
                 if l >= sg["nslab"]:
-                    continue
-                m = sg["p0"] - 2 + l
-                if lane & 7 == 0:
+                    break
+            else:
+                l = 4 * g + hi
+                k = sg["p0"] - 2 + l + (2 if lo == 0 else -3)
+                sub, bsel = lo, 1 - lo
+            slab_ok = l < sg["nslab"]
+            m = sg["p0"] - 2 + l
+            pair_ok = slab_ok and sg["p0"] <= k < sg["p1"]
+            if rr < 8:
+                if lane == 0:
                     slab_arr[(cta, sg["j0"] + l)] += 1
-                k = m + 2 if half == 0 else m - 3
-                if not (sg["p0"] <= k < sg["p1"]):
-                    continue
-                if lane & 3 == 0:
+                if pair_ok and lane & 15 == 0:
                     pair_arr[(cta, sg["a0"] + k - sg["p0"])] += 1
-                ya, yb, dyi = 2 * k + half, 2 * m - 1 + (1 - half), (0 if half == 0 else 8)
-                assert yb - ya == dyi - 4
-                for p in range(PX):
-                    x = sg["x0"] + xg * PX + p
-                    if ya < H and x < W:
-                        written[(sg["b"], ya, x, dyi)] += 1
+            else:
+                if slab_ok and lane & 7 == 0:
+                    slab_arr[(cta, sg["j0"] + l)] += 1
+                if pair_ok and lane & 6 == 0:
+                    pair_arr[(cta, sg["a0"] + k - sg["p0"])] += 1
+            yb, ya = 2 * m - 1 + bsel, 2 * k + sub
+            if not (pair_ok and ya < H):
+                continue
+            dyi = yb - ya + 4
+            assert 0 <= dyi <= 8
+            for p in range(PX):
+                x = sg["x0"] + xg * PX + p
+                if x < W:
+                    written[(sg["b"], ya, x, dyi)] += 1
     return segs
 
 
@@ -89,6 +84,6 @@ def test_stream_schedule_covers_every_output_once(B, H, W, grid):
         nslab += sum(s["nslab"] for s in segs)
         npair += sum(s["p1"] - s["p0"] for s in segs)
     assert len(written) == B * H * W * 9 and set(written.values()) == {1}
-    assert len(slab_arr) == nslab and set(slab_arr.values()) == {2}
+    assert len(slab_arr) == nslab and set(slab_arr.values()) == {3}
     assert len(pair_arr) == npair and set(pair_arr.values()) == {6}
     assert npair == B * ((W + TW - 1) // TW) * ((H + 1) // 2)

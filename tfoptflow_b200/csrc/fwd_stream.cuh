@@ -24,7 +24,7 @@ namespace stream {
 
 constexpr int R = 4, ND = 9, D = 81;
 constexpr int PX = 8, NXG = 4, TW = PX * NXG;  // 32-pixel strips
-constexpr int NCW = 4;                          // compute warps
+constexpr int NCW = 8;                          // compute warps
 constexpr int NPW = 4;                          // producer warps
 constexpr int NTHREADS = 32 * (NCW + NPW);
 constexpr int NPROD = 32 * NPW;
@@ -32,6 +32,7 @@ constexpr int BU = TW + 2 * R;                  // 40 warped pixels per row
 constexpr int B_USLOTS = BU + BU / PX - 1;      // 44 (slot(u) = u + u/8)
 constexpr int A_ROWSLOTS = TW + TW / PX;        // 36
 constexpr int MAXSEG = 8;
+constexpr int TASKS_PER_GROUP = 9;               // Fa,Fb for 4 slabs + 1 edge task
 
 template <int KV>
 struct Geo {
@@ -39,8 +40,8 @@ struct Geo {
   static constexpr int A_PLANE = A_ROWSLOTS * 2 + 1;    // 73
   static constexpr int BSLOT = KV * B_PLANE;            // float4 per slab slot
   static constexpr int ASLOT = KV * A_PLANE;            // float4 per pair slot
-  static constexpr int NSLAB = KV == 8 ? 8 : 12;        // ring depths
-  static constexpr int NAP = KV == 8 ? 13 : 18;
+  static constexpr int NSLAB = KV == 8 ? 7 : 12;        // ring depths
+  static constexpr int NAP = KV == 8 ? 12 : 18;
   static constexpr int STAGE_WORDS = 640;               // per compute warp (2 x 320, double buffered)
   static constexpr size_t OFF_B = 0;
   static constexpr size_t OFF_A = OFF_B + (size_t)NSLAB * BSLOT * 16;
@@ -90,7 +91,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // ---- producer ------------------------------------------------------------------------------
 template <int KV, typename T, typename TF>
 __device__ __forceinline__ void produce_pair(const T* __restrict__ c1, const Params& P, const Seg& sg, int k,
-                                             float4* __restrict__ sA_slot, int ptid) {
+                                             float4* __restrict__ sA_slot, int ptid, float inv_c) {
   // rows 2k, 2k+1 of the strip: 2 x 32 pixels x KV vectors
   constexpr int ITEMS = 2 * TW * KV;
 #pragma unroll
@@ -101,6 +102,7 @@ __device__ __forceinline__ void produce_pair(const T* __restrict__ c1, const Par
     const int y = 2 * k + row, x = sg.x0 + col;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (y < P.H && x < P.W) v = ld4(c1 + (((size_t)sg.b * P.H + y) * P.W + x) * P.C + 4 * kv);
+    v.x *= inv_c; v.y *= inv_c; v.z *= inv_c; v.w *= inv_c;  // mean over channels folded in (exact: C = 2^n)
     sA_slot[kv * Geo<KV>::A_PLANE + row * A_ROWSLOTS + col + col / PX] = v;
   }
 }
@@ -165,32 +167,27 @@ __device__ __forceinline__ void produce_slab(const T* __restrict__ c2, const TF*
   }
 }
 
-// ---- per-lane correlation: NSUB rows x 8 pixels x 9 dx against ONE warped row ---------------
-template <int KV, int NSUB>
-__device__ __forceinline__ void correlate(const float4* __restrict__ a0p, const float4* __restrict__ a1p,
-                                          const float4* __restrict__ bp, float (&acc)[NSUB][PX][ND]) {
+// ---- per-lane correlation: 1 row x 8 pixels x 9 dx against ONE warped row --------------------
+template <int KV>
+__device__ __forceinline__ void correlate(const float4* __restrict__ ap, const float4* __restrict__ bp,
+                                          float (&acc)[PX][ND]) {
 #pragma unroll 1
   for (int kv = 0; kv < KV; ++kv) {
-    // pixel-major order: the warped window slides (9 live float4), c1 operands live for one pixel only
+    // pixel-major order: the warped window slides (9 live float4), the c1 operand lives for one pixel only
     float4 bw[PX + 2 * R];
 #pragma unroll
     for (int k = 0; k < ND; ++k) bw[k] = bp[kv * Geo<KV>::B_PLANE + (k + k / PX) * 2];
 #pragma unroll
     for (int p = 0; p < PX; ++p) {
       if (p > 0) bw[p + ND - 1] = bp[kv * Geo<KV>::B_PLANE + ((p + ND - 1) + (p + ND - 1) / PX) * 2];
-      const float4 a0 = a0p[kv * Geo<KV>::A_PLANE + p];
-      float4 a1 = a0;
-      if (NSUB == 2) a1 = a1p[kv * Geo<KV>::A_PLANE + p];
+      const float4 a = ap[kv * Geo<KV>::A_PLANE + p];
 #pragma unroll
-      for (int d = 0; d < ND; ++d) {
-        fma4(acc[0][p][d], a0, bw[p + d]);
-        if (NSUB == 2) fma4(acc[NSUB - 1][p][d], a1, bw[p + d]);
-      }
+      for (int d = 0; d < ND; ++d) fma4(acc[p][d], a, bw[p + d]);
     }
   }
 }
 
-template <int KV, typename T, typename TF>
+template <int KV, bool DENSE, typename T, typename TF>
 __global__ void __launch_bounds__(NTHREADS, 1)
 fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* __restrict__ flow,
                   T* __restrict__ out, const Params P) {
@@ -209,7 +206,7 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int i = 0; i < G::NSLAB; ++i) { mbar_init(&fullB[i], NPROD); mbar_init(&emptyB[i], 2); }
+    for (int i = 0; i < G::NSLAB; ++i) { mbar_init(&fullB[i], NPROD); mbar_init(&emptyB[i], 3); }
     for (int i = 0; i < G::NAP; ++i) { mbar_init(&fullA[i], NPROD); mbar_init(&emptyA[i], 6); }
     // this CTA's contiguous range of (strip, pair) units, cut into per-strip segments
     const long long qlo = P.Q * blockIdx.x / gridDim.x, qhi = P.Q * (blockIdx.x + 1) / gridDim.x;
@@ -225,7 +222,7 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
       s.x0 = (int)(strip % P.nstrip_x) * TW;
       s.p0 = p0; s.p1 = p1; s.nslab = p1 - p0 + 5;
       s.task0 = task; s.j0 = j; s.a0 = a;
-      task += 5 * ((s.nslab + 3) / 4);
+      task += TASKS_PER_GROUP * ((s.nslab + 3) / 4);
       j += s.nslab;
       a += p1 - p0;
       segs[n++] = s;
@@ -245,7 +242,7 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
         if (sg.p0 + l < sg.p1) {
           const int ag = sg.a0 + l, slot = ag % G::NAP, use = ag / G::NAP;
           mbar_wait(&emptyA[slot], (use & 1) ^ 1);
-          produce_pair<KV, T, TF>(c1, P, sg, sg.p0 + l, sA + (size_t)slot * G::ASLOT, ptid);
+          produce_pair<KV, T, TF>(c1, P, sg, sg.p0 + l, sA + (size_t)slot * G::ASLOT, ptid, 1.0f / (float)P.C);
           mbar_arrive(&fullA[slot]);
         }
         const int jg = sg.j0 + l, slot = jg % G::NSLAB, use = jg / G::NSLAB;
@@ -260,10 +257,16 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
   }
 
   // =========================== compute warps ===========================
+  // Every task is 32 independent lane-tasks: (one c1 row, one warped row, 8 pixels, 9 dx) -> a run of 9
+  // output channels for each of 8 pixels.  The three task kinds differ only in the lane -> work mapping:
+  //   Fa(l): slab l vs c1 rows 2m-4 .. 2m-1      Fb(l): slab l vs c1 rows 2m .. 2m+3
+  //          lane = bsel + 2*xg + 8*rq   (bsel: warped row 2m-1 / 2m;  rq: c1 row within the 4)
+  //   E(g):  the two displacements out of reach of the 8-row window, for the 4 slabs of group g
+  //          lane = half + 2*xg + 8*ms   (half 0: c1 row 2m+4 vs warped row 2m, dy=-4;
+  //                                       half 1: c1 row 2m-5 vs warped row 2m-1, dy=+4)
   float* stage = sStage + warp * G::STAGE_WORDS;
-  const float inv_c = 1.0f / (float)P.C;
   const int total_tasks = s_misc[1];
-  const int xg = lane & 3;
+  const int xg = (lane >> 1) & 3, lo = lane & 1, hi = lane >> 3;
   while (true) {
     int t = 0;
     if (lane == 0) t = atomicAdd(&s_misc[2], 1);
@@ -272,131 +275,80 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
     int si = 0;
     while (si + 1 < nseg && segs[si + 1].task0 <= t) ++si;
     const Seg sg = segs[si];
-    const int tl = t - sg.task0, g = tl / 5, rr = tl - 5 * g;
+    const int tl = t - sg.task0, g = tl / TASKS_PER_GROUP, rr = tl - TASKS_PER_GROUP * g;
 
-    if (rr < 4) {
-      // ------------------------- full task F(l) -------------------------
-      const int l = 4 * g + rr;
-      if (l >= sg.nslab) continue;
-      const int m = sg.p0 - 2 + l;
-      const int bsel = (lane >> 2) & 1, pk = lane >> 3;
-      const int k = m - 2 + pk;
-      const bool pair_ok = (k >= sg.p0) && (k < sg.p1);
-      const int jg = sg.j0 + l, sb = jg % G::NSLAB;
-      const int ag = sg.a0 + (pair_ok ? k - sg.p0 : 0), sa = ag % G::NAP;
-      mbar_wait(&fullB[sb], (jg / G::NSLAB) & 1);
-      if (pair_ok) mbar_wait(&fullA[sa], (ag / G::NAP) & 1);
-      const int yb = 2 * m - 1 + bsel;
-      const bool active = pair_ok && yb >= 0 && yb < P.H;
-
-      float acc[2][PX][ND];
-#pragma unroll
-      for (int s = 0; s < 2; ++s)
-#pragma unroll
-        for (int p = 0; p < PX; ++p)
-#pragma unroll
-          for (int d = 0; d < ND; ++d) acc[s][p][d] = 0.f;
-      if (active) {
-        const float4* ap = sA + (size_t)sa * G::ASLOT + xg * (PX + 1);
-        const float4* bp = sB + (size_t)sb * G::BSLOT + xg * (PX + 1) * 2 + bsel;
-        correlate<KV, 2>(ap, ap + A_ROWSLOTS, bp, acc);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&emptyB[sb]);
-      if (pair_ok && (lane & 7) == 0) mbar_arrive(&emptyA[sa]);
-
-      // epilogue: per (row s, pixel p) the warp holds 16 runs of 18 contiguous channels.  Everything that
-      // does not depend on (s, p) is hoisted: element it*32+lane of the 288-float staging block.
-      size_t off[9];
-      int sidx[9], nvx[9], nvy[9];
-#pragma unroll
-      for (int it = 0; it < 9; ++it) {
-        const int idx = it * 32 + lane;
-        const int g2 = idx / 18, w = idx - g2 * 18;
-        const int pk2 = g2 >> 2, xg2 = g2 & 3;
-        const int k2 = m - 2 + pk2;
-        const bool ok = k2 >= sg.p0 && k2 < sg.p1;
-        const int xb = sg.x0 + xg2 * PX, y0 = 2 * k2;
-        nvx[it] = ok ? P.W - xb : 0;
-        nvy[it] = P.H - y0;
-        off[it] = (((size_t)sg.b * P.H + (ok ? y0 : 0)) * P.W + xb) * P.ops + (7 - 2 * pk2) * ND + w;
-        sidx[it] = g2 * 19 + w;
-      }
-      const int grp19 = (pk * 4 + xg) * 19 + bsel * 9;
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-#pragma unroll
-        for (int p = 0; p < PX; ++p) {
-          float* stg = stage + ((s * PX + p) & 1) * 320;
-#pragma unroll
-          for (int d = 0; d < ND; ++d) stg[grp19 + d] = lrelu01(acc[s][p][d] * inv_c);
-          __syncwarp();
-          const size_t sp = ((size_t)s * P.W + p) * P.ops - (size_t)(s * ND);
-#pragma unroll
-          for (int it = 0; it < 9; ++it)
-            if (p < nvx[it] && s < nvy[it]) out[off[it] + sp] = ElemTraits<T>::from_f(stg[sidx[it]]);
-        }
-      }
-      __syncwarp();
+    int l, k, sub, bsel;  // slab (segment-local), c1 pair, row within pair, warped row within slab
+    if (rr < 8) {
+      l = 4 * g + (rr >> 1);
+      k = sg.p0 - 2 + l - 2 + 2 * (rr & 1) + (hi >> 1);
+      sub = hi & 1;
+      bsel = lo;
     } else {
-      // ------------------------- edge task E(g): slabs 4g .. 4g+3 -------------------------
-      const int half = (lane >> 2) & 1, ms = lane >> 3;
-      const int l = 4 * g + ms;
-      const bool slab_ok = l < sg.nslab;
-      const int m = sg.p0 - 2 + l;
-      // half 0: row 2m+4 (pair m+2, sub 0) vs warped row 2m   (bsel 1), dy = -4 -> dyi 0
-      // half 1: row 2m-5 (pair m-3, sub 1) vs warped row 2m-1 (bsel 0), dy = +4 -> dyi 8
-      const int k = half == 0 ? m + 2 : m - 3;
-      const int sub = half, bsel = 1 - half;
-      const bool pair_ok = slab_ok && k >= sg.p0 && k < sg.p1;
-      const int jg = sg.j0 + (slab_ok ? l : 0), sb = jg % G::NSLAB;
-      const int ag = sg.a0 + (pair_ok ? k - sg.p0 : 0), sa = ag % G::NAP;
-      if (slab_ok) mbar_wait(&fullB[sb], (jg / G::NSLAB) & 1);
-      if (pair_ok) mbar_wait(&fullA[sa], (ag / G::NAP) & 1);
-      const int yb = 2 * m - 1 + bsel, ya = 2 * k + sub;
-      const bool active = pair_ok && yb >= 0 && yb < P.H && ya < P.H;
-
-      float acc[1][PX][ND];
-#pragma unroll
-      for (int p = 0; p < PX; ++p)
-#pragma unroll
-        for (int d = 0; d < ND; ++d) acc[0][p][d] = 0.f;
-      if (active) {
-        const float4* ap = sA + (size_t)sa * G::ASLOT + sub * A_ROWSLOTS + xg * (PX + 1);
-        const float4* bp = sB + (size_t)sb * G::BSLOT + xg * (PX + 1) * 2 + bsel;
-        correlate<KV, 1>(ap, ap, bp, acc);
-      }
-      __syncwarp();
-      if (slab_ok && (lane & 7) == 0) mbar_arrive(&emptyB[sb]);          // one arrival per slab (half 0, xg 0)
-      if (pair_ok && (lane & 3) == 0) mbar_arrive(&emptyA[sa]);           // one per (slab, half)
-
-      size_t off[9];
-      int nvx[9];
-#pragma unroll
-      for (int it = 0; it < 9; ++it) {
-        const int idx = it * 32 + lane;
-        const int l2 = idx / 9, w = idx - l2 * 9;  // source lane, channel within its run
-        const int xg2 = l2 & 3, half2 = (l2 >> 2) & 1, ms2 = l2 >> 3;
-        const int sl2 = 4 * g + ms2, m2 = sg.p0 - 2 + sl2;
-        const int k2 = half2 == 0 ? m2 + 2 : m2 - 3;
-        const int y = 2 * k2 + half2, xb = sg.x0 + xg2 * PX;
-        const bool ok = sl2 < sg.nslab && k2 >= sg.p0 && k2 < sg.p1 && y < P.H;
-        nvx[it] = ok ? P.W - xb : 0;
-        off[it] = (((size_t)sg.b * P.H + (ok ? y : 0)) * P.W + xb) * P.ops + (half2 == 0 ? 0 : 8) * ND + w;
-      }
-#pragma unroll
-      for (int p = 0; p < PX; ++p) {
-        float* stg = stage + (p & 1) * 320;
-#pragma unroll
-        for (int d = 0; d < ND; ++d) stg[lane * 9 + d] = lrelu01(acc[0][p][d] * inv_c);
-        __syncwarp();
-        const size_t sp = (size_t)p * P.ops;
-#pragma unroll
-        for (int it = 0; it < 9; ++it)
-          if (p < nvx[it]) out[off[it] + sp] = ElemTraits<T>::from_f(stg[it * 32 + lane]);
-      }
-      __syncwarp();
+      l = 4 * g + hi;
+      k = sg.p0 - 2 + l + (lo == 0 ? 2 : -3);
+      sub = lo;
+      bsel = 1 - lo;
     }
+    if (rr < 8 && l >= sg.nslab) continue;  // null task of a ragged last group (warp-uniform)
+    const bool slab_ok = l < sg.nslab;
+    const int m = sg.p0 - 2 + l;
+    const bool pair_ok = slab_ok && k >= sg.p0 && k < sg.p1;
+    const int jg = sg.j0 + (slab_ok ? l : 0), sb = jg % G::NSLAB;
+    const int ag = sg.a0 + (pair_ok ? k - sg.p0 : 0), sa = ag % G::NAP;
+    if (slab_ok) mbar_wait(&fullB[sb], (jg / G::NSLAB) & 1);
+    if (pair_ok) mbar_wait(&fullA[sa], (ag / G::NAP) & 1);
+    const int yb = 2 * m - 1 + bsel, ya = 2 * k + sub;
+    const bool store = pair_ok && ya < P.H;
+    const bool active = store && yb >= 0 && yb < P.H;
+
+    float acc[PX][ND];
+#pragma unroll
+    for (int p = 0; p < PX; ++p)
+#pragma unroll
+      for (int d = 0; d < ND; ++d) acc[p][d] = 0.f;
+    if (active) {
+      const float4* ap = sA + (size_t)sa * G::ASLOT + sub * A_ROWSLOTS + xg * (PX + 1);
+      const float4* bp = sB + (size_t)sb * G::BSLOT + xg * (PX + 1) * 2 + bsel;
+      correlate<KV>(ap, bp, acc);
+    }
+    __syncwarp();
+    // release the ring slots: one arrival per (task, slab) and per (task, pair)
+    if (rr < 8) {
+      if (lane == 0) mbar_arrive(&emptyB[sb]);
+      if (pair_ok && (lane & 15) == 0) mbar_arrive(&emptyA[sa]);
+    } else {
+      if (slab_ok && (lane & 7) == 0) mbar_arrive(&emptyB[sb]);
+      if (pair_ok && (lane & 6) == 0) mbar_arrive(&emptyA[sa]);
+    }
+
+    // epilogue: lane L owns, for each pixel p, the 9 channels [dyi*9, dyi*9+9) of pixel (ya, xb+p).
+    // Runs go through a per-warp transposition buffer so that each store instruction writes whole runs.
+    const int xb = sg.x0 + xg * PX;
+    const int dyi = yb - ya + R;
+    const long long my_off = store ? (long long)((((size_t)sg.b * P.H + ya) * P.W + xb) * P.ops + dyi * ND) : 0;
+    const int my_nv = store ? P.W - xb : 0;
+    T* optr[9];
+    int nv[9];
+#pragma unroll
+    for (int it = 0; it < 9; ++it) {
+      const int idx = it * 32 + lane;
+      const int l2 = idx / 9, w = idx - l2 * 9;
+      const long long o = __shfl_sync(0xffffffffu, my_off, l2);
+      nv[it] = __shfl_sync(0xffffffffu, my_nv, l2);
+      optr[it] = out + o + w;
+    }
+    const size_t pstride = DENSE ? (size_t)D : (size_t)P.ops;
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+      float* stg = stage + (p & 1) * (G::STAGE_WORDS / 2);
+#pragma unroll
+      for (int d = 0; d < ND; ++d) stg[lane * 9 + d] = fmaxf(0.1f * acc[p][d], acc[p][d]);
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 9; ++it)
+        if (p < nv[it]) optr[it][p * pstride] = ElemTraits<T>::from_f(stg[it * 32 + lane]);
+    }
+    __syncwarp();
   }
 }
 
@@ -416,18 +368,18 @@ int launch(const T* c1, const T* c2, const TF* flow, float flow_scale, T* out, i
   // every CTA must fit its range into MAXSEG per-strip segments
   const long long per = (P.Q + grid - 1) / grid;
   if (per / P.NPAIR + 2 > MAXSEG) return 1;
-  cudaError_t e;
-  if (C == 32) {
-    auto k = fwd_stream_kernel<8, T, TF>;
-    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<8>::SMEM_BYTES);
-    if (e != cudaSuccess) return -1;
-    k<<<(unsigned)grid, NTHREADS, Geo<8>::SMEM_BYTES, st>>>(c1, c2, flow, out, P);
-  } else {
-    auto k = fwd_stream_kernel<4, T, TF>;
-    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<4>::SMEM_BYTES);
-    if (e != cudaSuccess) return -1;
-    k<<<(unsigned)grid, NTHREADS, Geo<4>::SMEM_BYTES, st>>>(c1, c2, flow, out, P);
-  }
+  const bool dense = ops == D;
+  auto go = [&](auto kern, size_t smem_bytes) -> int {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) return -1;
+    kern<<<(unsigned)grid, NTHREADS, smem_bytes, st>>>(c1, c2, flow, out, P);
+    return 0;
+  };
+  int rc;
+  if (C == 32) rc = dense ? go(fwd_stream_kernel<8, true, T, TF>, Geo<8>::SMEM_BYTES)
+                          : go(fwd_stream_kernel<8, false, T, TF>, Geo<8>::SMEM_BYTES);
+  else         rc = dense ? go(fwd_stream_kernel<4, true, T, TF>, Geo<4>::SMEM_BYTES)
+                          : go(fwd_stream_kernel<4, false, T, TF>, Geo<4>::SMEM_BYTES);
+  if (rc) return rc;
   return 0;
 }
 
