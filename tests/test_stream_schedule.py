@@ -3,6 +3,10 @@ slab / pair rings, full tasks F and edge tasks E.  Checks that every (pixel, dy)
 exactly once from the right (c1 row, warped row) combination and that every ring slot gets exactly the number of
 consumer arrivals its mbarrier was initialised with (3 per slab, 6 per pair)."""
 import collections
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 import pytest
 
@@ -87,3 +91,18 @@ def test_stream_schedule_covers_every_output_once(B, H, W, grid):
     assert len(slab_arr) == nslab and set(slab_arr.values()) == {3}
     assert len(pair_arr) == npair and set(pair_arr.values()) == {6}
     assert npair == B * ((W + TW - 1) // TW) * ((H + 1) // 2)
+
+
+@pytest.mark.parametrize("cfg", [(7, 12, 8, 8), (7, 12, 4, 8), (12, 18, 8, 8)])
+def test_ring_protocol_has_no_deadlock_or_hazard(cfg):
+    """Random adversarial schedules with long stalls against exact mbarrier parity semantics (two barrier sets)."""
+    from stream_protocol_sim import simulate
+    for seed in range(4):
+        assert simulate(40, *cfg, BARMUL=2, seed=seed) == "ok"
+
+
+def test_single_barrier_set_is_unsafe():
+    """Documents why the kernel uses two alternating barrier sets: one set lets a consumer pass a parity wait early."""
+    from stream_protocol_sim import simulate
+    res = [simulate(40, 7, 12, 8, 8, BARMUL=1, seed=s) for s in range(6)]
+    assert any(r.startswith("hazard") for r in res)

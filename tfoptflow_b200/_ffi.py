@@ -10,7 +10,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libpwc_b200.so")
+LIB_PATH = os.environ.get("PWC_B200_LIB") or os.path.join(_HERE, "_lib", "libpwc_b200.so")
 
 PWC_F32, PWC_F16, PWC_BF16 = 0, 1, 2
 ABI_VERSION = 1

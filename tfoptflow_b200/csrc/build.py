@@ -25,17 +25,18 @@ def _stale() -> bool:
     return False
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, out: str | None = None, extra_defs=()) -> str:
+    if out is None and not force and not _stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
+    lib_path = out or LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     defs = []
     if os.path.exists(os.path.join(HERE, "fwd_stream.cuh")):
         defs.append("-DPWC_HAVE_STREAM_KERNEL")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "--use_fast_math" if False else "-DPWC_NO_FAST_MATH", "-Xcompiler", "-fPIC,-O2", "-shared",
-           "-cudart", "static", "-o", LIB_PATH] + defs
+           "-cudart", "static", "-o", lib_path] + defs + list(extra_defs)
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [os.path.join(HERE, s) for s in SOURCES]
@@ -45,7 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed building libpwc_b200.so")
     if verbose:
         sys.stderr.write(r.stdout + r.stderr)
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":

@@ -22,10 +22,19 @@
 namespace pwc {
 namespace stream {
 
+#ifndef PWC_STREAM_LD4
+#define PWC_STREAM_LD4 ld4
+#endif
+#define LD4 PWC_STREAM_LD4
+
 constexpr int R = 4, ND = 9, D = 81;
 constexpr int PX = 8, NXG = 4, TW = PX * NXG;  // 32-pixel strips
 constexpr int NCW = 8;                          // compute warps
-constexpr int NPW = 4;                          // producer warps
+#ifndef PWC_STREAM_NPW
+#define PWC_STREAM_NPW 4
+#endif
+constexpr int NPW = PWC_STREAM_NPW;             // producer warps
+constexpr int REGS_COMPUTE = 168, REGS_PRODUCER = 88;  // setmaxnreg budgets (NPW == 8: 256*168 + 256*88 = 64K)
 constexpr int NTHREADS = 32 * (NCW + NPW);
 constexpr int NPROD = 32 * NPW;
 constexpr int BU = TW + 2 * R;                  // 40 warped pixels per row
@@ -40,14 +49,19 @@ struct Geo {
   static constexpr int A_PLANE = A_ROWSLOTS * 2 + 1;    // 73
   static constexpr int BSLOT = KV * B_PLANE;            // float4 per slab slot
   static constexpr int ASLOT = KV * A_PLANE;            // float4 per pair slot
-  static constexpr int NSLAB = KV == 8 ? 7 : 12;        // ring depths
-  static constexpr int NAP = KV == 8 ? 12 : 18;
+#ifndef PWC_STREAM_NSLAB
+#define PWC_STREAM_NSLAB 7
+#define PWC_STREAM_NAP 12
+#endif
+  static constexpr int NSLAB = KV == 8 ? PWC_STREAM_NSLAB : 12;        // ring depths
+  static constexpr int NAP = KV == 8 ? PWC_STREAM_NAP : 18;
   static constexpr int STAGE_WORDS = 640;               // per compute warp (2 x 320, double buffered)
   static constexpr size_t OFF_B = 0;
   static constexpr size_t OFF_A = OFF_B + (size_t)NSLAB * BSLOT * 16;
   static constexpr size_t OFF_STAGE = OFF_A + (size_t)NAP * ASLOT * 16;
-  static constexpr size_t OFF_BAR = OFF_STAGE + (size_t)NCW * STAGE_WORDS * 4;
-  static constexpr size_t OFF_SEG = OFF_BAR + (size_t)(2 * NSLAB + 2 * NAP) * 8;
+  static constexpr size_t OFF_SCRATCH = OFF_STAGE + (size_t)NCW * STAGE_WORDS * 4;
+  static constexpr size_t OFF_BAR = OFF_SCRATCH + (size_t)NPW * 2 * BU * 16;
+  static constexpr size_t OFF_SEG = OFF_BAR + (size_t)(4 * NSLAB + 4 * NAP) * 8;
   static constexpr size_t SMEM_BYTES = OFF_SEG + MAXSEG * 32 + 64;
 };
 
@@ -64,6 +78,8 @@ struct Params {
   int NPAIR;        // ceil(H / 2)
   int nstrip_x;     // ceil(W / TW)
   long long Q;      // total (strip, pair) units
+  int pf_dist;      // L2 prefetch distance in slabs (0 = off)
+  int dbg;          // timing experiments only: 1 = skip correlate, 2 = skip gathers, 4 = skip stores
 };
 
 // ---- mbarrier helpers (generic-proxy producers/consumers only) ---------------------------
@@ -89,82 +105,131 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ---- producer ------------------------------------------------------------------------------
-template <int KV, typename T, typename TF>
+// Each producer warp owns every NPW-th slab of the CTA's sequence (and the c1 pair that travels with it),
+// so NPW slabs are being gathered at any time and their global-memory latencies overlap.
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+template <int KV, typename T>
 __device__ __forceinline__ void produce_pair(const T* __restrict__ c1, const Params& P, const Seg& sg, int k,
-                                             float4* __restrict__ sA_slot, int ptid, float inv_c) {
-  // rows 2k, 2k+1 of the strip: 2 x 32 pixels x KV vectors
-  constexpr int ITEMS = 2 * TW * KV;
+                                             float4* __restrict__ sA_slot, int lane, float inv_c) {
+  // rows 2k, 2k+1 of the strip: 2 x 32 pixels x KV vectors, KV lanes per pixel
+  constexpr int ITEMS = 2 * TW * KV / 32;  // per lane
+  constexpr int BATCH = 8;
 #pragma unroll
-  for (int it = 0; it < ITEMS / NPROD; ++it) {
-    const int id = it * NPROD + ptid;
-    const int kv = id % KV, pxl = id / KV;
-    const int row = pxl / TW, col = pxl - row * TW;
-    const int y = 2 * k + row, x = sg.x0 + col;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (y < P.H && x < P.W) v = ld4(c1 + (((size_t)sg.b * P.H + y) * P.W + x) * P.C + 4 * kv);
-    v.x *= inv_c; v.y *= inv_c; v.z *= inv_c; v.w *= inv_c;  // mean over channels folded in (exact: C = 2^n)
-    sA_slot[kv * Geo<KV>::A_PLANE + row * A_ROWSLOTS + col + col / PX] = v;
+  for (int b0 = 0; b0 < ITEMS; b0 += BATCH) {
+    float4 v[BATCH];
+#pragma unroll
+    for (int it = 0; it < BATCH; ++it) {
+      const int id = (b0 + it) * 32 + lane;
+      const int kv = id % KV, pxl = id / KV;
+      const int row = pxl / TW, col = pxl - row * TW;
+      const int y = 2 * k + row, x = sg.x0 + col;
+      v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (y < P.H && x < P.W) v[it] = LD4(c1 + (((size_t)sg.b * P.H + y) * P.W + x) * P.C + 4 * kv);
+    }
+#pragma unroll
+    for (int it = 0; it < BATCH; ++it) {
+      const int id = (b0 + it) * 32 + lane;
+      const int kv = id % KV, pxl = id / KV;
+      const int row = pxl / TW, col = pxl - row * TW;
+      float4 w = v[it];
+      w.x *= inv_c; w.y *= inv_c; w.z *= inv_c; w.w *= inv_c;  // mean over channels folded in (exact: C = 2^n)
+      sA_slot[kv * Geo<KV>::A_PLANE + row * A_ROWSLOTS + col + col / PX] = w;
+    }
   }
 }
 
 template <int KV, typename T, typename TF>
 __device__ __forceinline__ void produce_slab(const T* __restrict__ c2, const TF* __restrict__ flow, const Params& P,
-                                             const Seg& sg, int m, float4* __restrict__ sB_slot, int pwarp, int lane) {
-  // warped rows 2m-1 (bsel 0) and 2m (bsel 1), u = 0..39 <-> x = x0 - 4 + u : 80 pixels, 20 per producer warp
-  constexpr int PPW = 2 * BU / NPW;   // 20 pixels per warp
-  constexpr int LPP = KV;             // lanes per pixel
-  constexpr int PPI = 32 / LPP;       // pixels per iteration
-  constexpr int NIT = (PPW + PPI - 1) / PPI;
-  // phase 1: lanes 0..19 compute the sampling coordinates of "their" pixel
-  int c_pix = 0, c_flag = 0;
-  float c_ax = 0.f, c_ay = 0.f;
-  if (lane < PPW) {
-    const int e = pwarp * PPW + lane;
-    const int bsel = e / BU, u = e - bsel * BU;
-    const int y = 2 * m - 1 + bsel, x = sg.x0 - R + u;
-    if (y >= 0 && y < P.H && x >= 0 && x < P.W) {
-      if (flow != nullptr) {
-        const SampleCoord s = sample_coord<T, TF>(flow, P.flow_scale, sg.b, y, x, P.H, P.W);
-        c_pix = s.pix; c_ax = s.ax; c_ay = s.ay; c_flag = 1;
-      } else {
-        c_pix = (sg.b * P.H + y) * P.W + x; c_flag = 2;
+                                             const Seg& sg, int m, float4* __restrict__ sB_slot,
+                                             int4* __restrict__ scratch, int lane) {
+  // warped rows 2m-1 (bsel 0) and 2m (bsel 1), u = 0..39 <-> x = x0 - 4 + u : 80 pixels
+  constexpr int NPIX = 2 * BU;
+  __syncwarp();  // every lane is done reading the previous slab's scratch
+  // phase 1: sampling coordinates of the 80 pixels -> per-warp scratch
+#pragma unroll
+  for (int e0 = 0; e0 < NPIX; e0 += 32) {
+    const int e = e0 + lane;
+    if (e < NPIX) {
+      const int bsel = e / BU, u = e - bsel * BU;
+      const int y = 2 * m - 1 + bsel, x = sg.x0 - R + u;
+      int4 cd = make_int4(0, 0, 0, 0);
+      if (y >= 0 && y < P.H && x >= 0 && x < P.W) {
+        if (flow != nullptr) {
+          const SampleCoord s = sample_coord<T, TF>(flow, P.flow_scale, sg.b, y, x, P.H, P.W);
+          cd = make_int4(s.pix, __float_as_int(s.ax), __float_as_int(s.ay), 1);
+        } else {
+          cd = make_int4((sg.b * P.H + y) * P.W + x, 0, 0, 2);
+        }
       }
+      scratch[e] = cd;
     }
   }
-  // phase 2: LPP lanes per pixel gather the 4 corners (full pixel vectors) and lerp
-  const int kv = lane % LPP, sub = lane / LPP;
-  float4 tl[NIT], tr[NIT], bl[NIT], br[NIT];
-  int flag[NIT];
-  float ax[NIT], ay[NIT];
+  __syncwarp();
+  // phase 2: KV lanes per pixel gather the 4 corners (full pixel vectors) and lerp
+  constexpr int PPI = 32 / KV;        // pixels per iteration
+  constexpr int NIT = NPW == 8 ? 2 : 5;  // iterations per batch (all loads of a batch are issued before any use)
+  constexpr int PXB = NIT * PPI;      // pixels per batch
+  static_assert(NPIX % PXB == 0, "batching");
+  const int kv = lane % KV, sub = lane / KV;
+#pragma unroll 1
+  for (int p0 = 0; p0 < NPIX; p0 += PXB) {
+    float4 tl[NIT], tr[NIT], bl[NIT], br[NIT];
+    int4 cd[NIT];
 #pragma unroll
-  for (int it = 0; it < NIT; ++it) {
-    const int pl = it * PPI + sub;  // local pixel
-    const int src = pl < PPW ? pl : 0;
-    const int pix = __shfl_sync(0xffffffffu, c_pix, src);
-    ax[it] = __shfl_sync(0xffffffffu, c_ax, src);
-    ay[it] = __shfl_sync(0xffffffffu, c_ay, src);
-    const int fl = __shfl_sync(0xffffffffu, c_flag, src);
-    flag[it] = pl < PPW ? fl : -1;
-    tl[it] = tr[it] = bl[it] = br[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (flag[it] > 0) {
-      const T* base = c2 + (size_t)pix * P.C + 4 * kv;
-      tl[it] = ld4(base);
-      if (flag[it] == 1) {
-        tr[it] = ld4(base + P.C);
-        bl[it] = ld4(base + (size_t)P.W * P.C);
-        br[it] = ld4(base + (size_t)P.W * P.C + P.C);
+    for (int it = 0; it < NIT; ++it) {
+      cd[it] = scratch[p0 + it * PPI + sub];
+      tl[it] = tr[it] = bl[it] = br[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (cd[it].w > 0) {
+        const T* base = c2 + (size_t)cd[it].x * P.C + 4 * kv;
+        tl[it] = LD4(base);
+        if (cd[it].w == 1) {
+          tr[it] = LD4(base + P.C);
+          bl[it] = LD4(base + (size_t)P.W * P.C);
+          br[it] = LD4(base + (size_t)P.W * P.C + P.C);
+        }
       }
     }
-  }
 #pragma unroll
-  for (int it = 0; it < NIT; ++it) {
-    if (flag[it] < 0) continue;
-    float4 v = tl[it];
-    if (flag[it] == 1) v = round4<T>(bilerp4(tl[it], tr[it], bl[it], br[it], ax[it], ay[it]));
-    const int e = pwarp * PPW + it * PPI + sub;
-    const int bsel = e / BU, u = e - bsel * BU;
-    sB_slot[kv * Geo<KV>::B_PLANE + (u + u / PX) * 2 + bsel] = v;
+    for (int it = 0; it < NIT; ++it) {
+      float4 v = tl[it];
+      if (cd[it].w == 1)
+        v = round4<T>(bilerp4(tl[it], tr[it], bl[it], br[it], __int_as_float(cd[it].y), __int_as_float(cd[it].z)));
+      const int e = p0 + it * PPI + sub;
+      const int bsel = e / BU, u = e - bsel * BU;
+      sB_slot[kv * Geo<KV>::B_PLANE + (u + u / PX) * 2 + bsel] = v;
+    }
   }
+}
+
+// pull the leading edge of a future slab (2 rows of c2, flow and c1) towards L2 with bulk prefetches
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+template <typename T, typename TF>
+__device__ __forceinline__ void prefetch_rows(const T* c1, const T* c2, const TF* flow, const Params& P, const Seg& sg,
+                                              int y0, int lane) {
+  // lanes 0,1: c2 rows y0, y0+1 ; lanes 2,3: c1 ; lanes 4,5: flow.  Ranges are rounded to 16 bytes.
+  const int r = lane & 1, what = lane >> 1;
+  const int y = y0 + r;
+  if (what > 2 || y < 0 || y >= P.H) return;
+  if (what == 2 && flow == nullptr) return;
+  const int xlo = max(sg.x0 - 8, 0), xhi = min(sg.x0 + TW + 8, P.W);
+  const size_t rowpix = ((size_t)sg.b * P.H + y) * P.W;
+  uintptr_t lo, hi;
+  if (what == 2) {
+    lo = reinterpret_cast<uintptr_t>(flow + (rowpix + xlo) * 2);
+    hi = reinterpret_cast<uintptr_t>(flow + (rowpix + xhi) * 2);
+  } else {
+    const T* base = what == 0 ? c2 : c1;
+    lo = reinterpret_cast<uintptr_t>(base + (rowpix + xlo) * P.C);
+    hi = reinterpret_cast<uintptr_t>(base + (rowpix + xhi) * P.C);
+  }
+  lo &= ~uintptr_t(15);
+  hi &= ~uintptr_t(15);  // round down: never touch bytes past the tensor
+  if (hi > lo) bulk_prefetch_l2(reinterpret_cast<const void*>(lo), (uint32_t)(hi - lo));
 }
 
 // ---- per-lane correlation: 1 row x 8 pixels x 9 dx against ONE warped row --------------------
@@ -197,17 +262,20 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
   float4* sA = reinterpret_cast<float4*>(smem + G::OFF_A);
   float* sStage = reinterpret_cast<float*>(smem + G::OFF_STAGE);
   uint64_t* fullB = reinterpret_cast<uint64_t*>(smem + G::OFF_BAR);
-  uint64_t* emptyB = fullB + G::NSLAB;
-  uint64_t* fullA = emptyB + G::NSLAB;
-  uint64_t* emptyA = fullA + G::NAP;
+  // Two alternating barrier sets per data slot (index j % 2N, parity (j / 2N) & 1): with one set a waiter that
+  // is two uses ahead of a slow producer would pass a parity wait prematurely (tests/stream_protocol_sim.py).
+  constexpr int NBB = 2 * G::NSLAB, NBA = 2 * G::NAP;
+  uint64_t* emptyB = fullB + NBB;
+  uint64_t* fullA = emptyB + NBB;
+  uint64_t* emptyA = fullA + NBA;
   Seg* segs = reinterpret_cast<Seg*>(smem + G::OFF_SEG);
   int* s_misc = reinterpret_cast<int*>(smem + G::OFF_SEG + MAXSEG * 32);  // [0] nseg, [1] total tasks, [2] task counter
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int i = 0; i < G::NSLAB; ++i) { mbar_init(&fullB[i], NPROD); mbar_init(&emptyB[i], 3); }
-    for (int i = 0; i < G::NAP; ++i) { mbar_init(&fullA[i], NPROD); mbar_init(&emptyA[i], 6); }
+    for (int i = 0; i < NBB; ++i) { mbar_init(&fullB[i], 32); mbar_init(&emptyB[i], 3); }
+    for (int i = 0; i < NBA; ++i) { mbar_init(&fullA[i], 32); mbar_init(&emptyA[i], 6); }
     // this CTA's contiguous range of (strip, pair) units, cut into per-strip segments
     const long long qlo = P.Q * blockIdx.x / gridDim.x, qhi = P.Q * (blockIdx.x + 1) / gridDim.x;
     int n = 0, task = 0, j = 0, a = 0;
@@ -235,22 +303,29 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
 
   if (warp >= NCW) {
     // =========================== producers ===========================
-    const int pwarp = warp - NCW, ptid = tid - 32 * NCW;
+    if (NPW == 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER));
+    const int pwarp = warp - NCW;
+    int4* scratch = reinterpret_cast<int4*>(smem + G::OFF_SCRATCH) + pwarp * (2 * BU);
+    const float inv_c = 1.0f / (float)P.C;
     for (int si = 0; si < nseg; ++si) {
       const Seg sg = segs[si];
       for (int l = 0; l < sg.nslab; ++l) {
-        if (sg.p0 + l < sg.p1) {
-          const int ag = sg.a0 + l, slot = ag % G::NAP, use = ag / G::NAP;
-          mbar_wait(&emptyA[slot], (use & 1) ^ 1);
-          produce_pair<KV, T, TF>(c1, P, sg, sg.p0 + l, sA + (size_t)slot * G::ASLOT, ptid, 1.0f / (float)P.C);
-          mbar_arrive(&fullA[slot]);
-        }
-        const int jg = sg.j0 + l, slot = jg % G::NSLAB, use = jg / G::NSLAB;
+        const int jg = sg.j0 + l;
+        if (jg % NPW != pwarp) continue;
         const int m = sg.p0 - 2 + l;
-        mbar_wait(&emptyB[slot], (use & 1) ^ 1);
-        if (2 * m >= 0 && 2 * m - 1 < P.H)  // slabs entirely outside the image are never read
-          produce_slab<KV, T, TF>(c2, flow, P, sg, m, sB + (size_t)slot * G::BSLOT, pwarp, lane);
-        mbar_arrive(&fullB[slot]);
+        // rows that the slab this warp will gather next (NPW slabs ahead) adds to the working set
+        if (P.pf_dist > 0) prefetch_rows<T, TF>(c1, c2, flow, P, sg, 2 * (m + P.pf_dist) + 2, lane);
+        if (sg.p0 + l < sg.p1) {
+          const int ag = sg.a0 + l, slot = ag % G::NAP, prev = ag - G::NAP;
+          if (prev >= 0) mbar_wait(&emptyA[prev % NBA], (prev / NBA) & 1);  // previous occupant fully consumed
+          if (!(P.dbg & 2)) produce_pair<KV, T>(c1, P, sg, sg.p0 + l, sA + (size_t)slot * G::ASLOT, lane, inv_c);
+          mbar_arrive(&fullA[ag % NBA]);
+        }
+        const int slot = jg % G::NSLAB, prev = jg - G::NSLAB;
+        if (prev >= 0) mbar_wait(&emptyB[prev % NBB], (prev / NBB) & 1);
+        if (2 * m >= 0 && 2 * m - 1 < P.H && !(P.dbg & 2))  // slabs entirely outside the image are never read
+          produce_slab<KV, T, TF>(c2, flow, P, sg, m, sB + (size_t)slot * G::BSLOT, scratch, lane);
+        mbar_arrive(&fullB[jg % NBB]);
       }
     }
     return;
@@ -264,6 +339,7 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
   //   E(g):  the two displacements out of reach of the 8-row window, for the 4 slabs of group g
   //          lane = half + 2*xg + 8*ms   (half 0: c1 row 2m+4 vs warped row 2m, dy=-4;
   //                                       half 1: c1 row 2m-5 vs warped row 2m-1, dy=+4)
+  if (NPW == 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_COMPUTE));
   float* stage = sStage + warp * G::STAGE_WORDS;
   const int total_tasks = s_misc[1];
   const int xg = (lane >> 1) & 3, lo = lane & 1, hi = lane >> 3;
@@ -295,8 +371,8 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
     const bool pair_ok = slab_ok && k >= sg.p0 && k < sg.p1;
     const int jg = sg.j0 + (slab_ok ? l : 0), sb = jg % G::NSLAB;
     const int ag = sg.a0 + (pair_ok ? k - sg.p0 : 0), sa = ag % G::NAP;
-    if (slab_ok) mbar_wait(&fullB[sb], (jg / G::NSLAB) & 1);
-    if (pair_ok) mbar_wait(&fullA[sa], (ag / G::NAP) & 1);
+    if (slab_ok) mbar_wait(&fullB[jg % NBB], (jg / NBB) & 1);
+    if (pair_ok) mbar_wait(&fullA[ag % NBA], (ag / NBA) & 1);
     const int yb = 2 * m - 1 + bsel, ya = 2 * k + sub;
     const bool store = pair_ok && ya < P.H;
     const bool active = store && yb >= 0 && yb < P.H;
@@ -306,7 +382,7 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
     for (int p = 0; p < PX; ++p)
 #pragma unroll
       for (int d = 0; d < ND; ++d) acc[p][d] = 0.f;
-    if (active) {
+    if (active && !(P.dbg & 1)) {
       const float4* ap = sA + (size_t)sa * G::ASLOT + sub * A_ROWSLOTS + xg * (PX + 1);
       const float4* bp = sB + (size_t)sb * G::BSLOT + xg * (PX + 1) * 2 + bsel;
       correlate<KV>(ap, bp, acc);
@@ -314,11 +390,11 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
     __syncwarp();
     // release the ring slots: one arrival per (task, slab) and per (task, pair)
     if (rr < 8) {
-      if (lane == 0) mbar_arrive(&emptyB[sb]);
-      if (pair_ok && (lane & 15) == 0) mbar_arrive(&emptyA[sa]);
+      if (lane == 0) mbar_arrive(&emptyB[jg % NBB]);
+      if (pair_ok && (lane & 15) == 0) mbar_arrive(&emptyA[ag % NBA]);
     } else {
-      if (slab_ok && (lane & 7) == 0) mbar_arrive(&emptyB[sb]);
-      if (pair_ok && (lane & 6) == 0) mbar_arrive(&emptyA[sa]);
+      if (slab_ok && (lane & 7) == 0) mbar_arrive(&emptyB[jg % NBB]);
+      if (pair_ok && (lane & 6) == 0) mbar_arrive(&emptyA[ag % NBA]);
     }
 
     // epilogue: lane L owns, for each pixel p, the 9 channels [dyi*9, dyi*9+9) of pixel (ya, xb+p).
@@ -346,7 +422,7 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
       __syncwarp();
 #pragma unroll
       for (int it = 0; it < 9; ++it)
-        if (p < nv[it]) optr[it][p * pstride] = ElemTraits<T>::from_f(stg[it * 32 + lane]);
+        if (p < nv[it] && !(P.dbg & 4)) optr[it][p * pstride] = ElemTraits<T>::from_f(stg[it * 32 + lane]);
     }
     __syncwarp();
   }
@@ -355,13 +431,15 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
 // Host-side launcher.  Returns 0 when launched, 1 when the shape is not covered, -1 on a CUDA error.
 template <typename T, typename TF>
 int launch(const T* c1, const T* c2, const TF* flow, float flow_scale, T* out, int B, int H, int W, int C,
-           int64_t ops, cudaStream_t st, int sms, int ctas_override) {
+           int64_t ops, cudaStream_t st, int sms, int ctas_override, int pf_dist, int dbg = 0) {
   if (C != 32 && C != 16) return 1;
   Params P;
   P.B = B; P.H = H; P.W = W; P.C = C; P.ops = ops; P.flow_scale = flow_scale;
   P.NPAIR = (H + 1) / 2;
   P.nstrip_x = (W + TW - 1) / TW;
   P.Q = (long long)B * P.nstrip_x * P.NPAIR;
+  P.pf_dist = pf_dist;
+  P.dbg = dbg;
   if (P.Q <= 0) return 1;
   long long grid = ctas_override > 0 ? ctas_override : sms;
   if (grid > P.Q) grid = P.Q;

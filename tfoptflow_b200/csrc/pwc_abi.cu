@@ -23,6 +23,8 @@ thread_local std::string g_err;
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_fwd_impl{0};
 std::atomic<int> g_stream_ctas{0};
+std::atomic<int> g_stream_pf{4};
+std::atomic<int> g_stream_dbg{0};
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -111,7 +113,7 @@ int fwd_typed(const void* c1, const void* c2, const void* flow, float flow_scale
 #ifdef PWC_HAVE_STREAM_KERNEL
   if (impl == 3) {
     int rc = pwc::stream::launch<T, TF>((const T*)c1, (const T*)c2, (const TF*)flow, flow_scale, (T*)out, B, H, W, C,
-                                        ops, st, dev.sms, g_stream_ctas.load());
+                                        ops, st, dev.sms, g_stream_ctas.load(), g_stream_pf.load(), g_stream_dbg.load());
     if (rc == 0) { PWC_LAUNCH_CHECK(); return PWC_OK; }
     if (rc < 0) return fail(PWC_ERR_CUDA, "stream kernel launch failed");
     impl = 2;  // rc > 0: shape not covered
@@ -341,12 +343,22 @@ int pwc_set_option(const char* key, int value) {
     g_stream_ctas.store(value);
     return PWC_OK;
   }
+  if (!strcmp(key, "stream_prefetch")) {
+    g_stream_pf.store(value);
+    return PWC_OK;
+  }
+  if (!strcmp(key, "stream_debug")) {  // timing experiments only; results are wrong when non-zero
+    g_stream_dbg.store(value);
+    return PWC_OK;
+  }
   return fail(PWC_ERR_BAD_ARG, "unknown option '%s'", key);
 }
 int pwc_get_option(const char* key, int* value) {
   if (!key || !value) return fail(PWC_ERR_BAD_ARG, "null argument");
   if (!strcmp(key, "fwd_impl")) { *value = g_fwd_impl.load(); return PWC_OK; }
   if (!strcmp(key, "stream_ctas")) { *value = g_stream_ctas.load(); return PWC_OK; }
+  if (!strcmp(key, "stream_prefetch")) { *value = g_stream_pf.load(); return PWC_OK; }
+  if (!strcmp(key, "stream_debug")) { *value = g_stream_dbg.load(); return PWC_OK; }
   return fail(PWC_ERR_BAD_ARG, "unknown option '%s'", key);
 }
 
