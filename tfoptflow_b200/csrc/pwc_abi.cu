@@ -7,6 +7,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "bwd.cuh"
@@ -108,14 +109,22 @@ int fwd_typed(const void* c1, const void* c2, const void* flow, float flow_scale
   const size_t va = sizeof(T) * 4;  // vector alignment for 4-element loads
   const bool vec_ok = (C % 4 == 0) && aligned(c1, va) && aligned(c2, va);
   int impl = g_fwd_impl.load();
-  if (impl == 0) impl = (r == 4 && vec_ok) ? 2 : 1;
-  if (impl >= 2 && !(r == 4 && vec_ok)) impl = 1;
+  const bool tuned_ok = r == 4 && vec_ok;
+  // auto: the streaming kernel wins on tall levels (it pays ~5 warm-up slabs per strip segment), the tiled kernel
+  // on short ones; measured crossover between H = 28 and H = 56 (profiles/r01_notes.md)
+  if (impl == 0) impl = !tuned_ok ? 1 : (H >= 40 ? 3 : 2);
+  if (impl >= 2 && !tuned_ok) impl = 1;
 #ifdef PWC_HAVE_STREAM_KERNEL
   if (impl == 3) {
-    int rc = pwc::stream::launch<T, TF>((const T*)c1, (const T*)c2, (const TF*)flow, flow_scale, (T*)out, B, H, W, C,
-                                        ops, st, dev.sms, g_stream_ctas.load(), g_stream_pf.load(), g_stream_dbg.load());
+    int rc = 1;
+    // instantiated for the dtype pairs the reference uses (fp32/fp32, fp16/fp16); others take the tiled kernel
+    if constexpr ((std::is_same<T, float>::value && std::is_same<TF, float>::value) ||
+                  (std::is_same<T, __half>::value && std::is_same<TF, __half>::value)) {
+      rc = pwc::stream::launch<T, TF>((const T*)c1, (const T*)c2, (const TF*)flow, flow_scale, (T*)out, B, H, W, C,
+                                      ops, st, dev.sms, g_stream_ctas.load(), g_stream_pf.load(), g_stream_dbg.load());
+    }
     if (rc == 0) { PWC_LAUNCH_CHECK(); return PWC_OK; }
-    if (rc < 0) return fail(PWC_ERR_CUDA, "stream kernel launch failed");
+    if (rc < 0) return fail(PWC_ERR_CUDA, "stream kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     impl = 2;  // rc > 0: shape not covered
   }
 #else
