@@ -112,12 +112,9 @@ __device__ __forceinline__ float query_coord<__nv_bfloat16>(int grid, __nv_bfloa
   return __bfloat162float(__double2bfloat16((double)grid - (double)s));
 }
 
-// TImg decides the dtype alpha is cast to (core_warp.py:112)
+// TImg decides the dtype alpha is cast to (core_warp.py:112).  f0 / f1: flow of the pixel (rows / columns).
 template <typename TImg, typename TF>
-__device__ __forceinline__ SampleCoord sample_coord(const TF* __restrict__ flow, float flow_scale,
-                                                    int b, int y, int x, int H, int W) {
-  const size_t p = ((size_t)b * H + y) * W + x;
-  const TF f0 = flow[2 * p], f1 = flow[2 * p + 1];
+__device__ __forceinline__ SampleCoord sample_coord_v(TF f0, TF f1, float flow_scale, int b, int y, int x, int H, int W) {
   const float qy = query_coord<TF>(y, f0, flow_scale);
   const float qx = query_coord<TF>(x, f1, flow_scale);
   const float fy = fminf(fmaxf(0.0f, floorf(qy)), (float)(H - 2));
@@ -135,6 +132,12 @@ __device__ __forceinline__ SampleCoord sample_coord(const TF* __restrict__ flow,
   s.ax = fminf(fmaxf(0.0f, ax), 1.0f);
   s.pix = (b * H + (int)fy) * W + (int)fx;
   return s;
+}
+template <typename TImg, typename TF>
+__device__ __forceinline__ SampleCoord sample_coord(const TF* __restrict__ flow, float flow_scale,
+                                                    int b, int y, int x, int H, int W) {
+  const size_t p = ((size_t)b * H + y) * W + x;
+  return sample_coord_v<TImg, TF>(flow[2 * p], flow[2 * p + 1], flow_scale, b, y, x, H, W);
 }
 
 // lerp exactly as the reference evaluates it: alpha * (hi - lo) + lo with three roundings

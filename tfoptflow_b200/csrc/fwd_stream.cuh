@@ -177,12 +177,56 @@ __device__ __forceinline__ float4 bilerp4_fast(const float4& tl, const float4& t
 }
 
 // warped rows 2m-1 (bsel 0) and 2m (bsel 1), u = 0..BU-1 <-> x = x0 - 4 + u
+template <typename G, bool HAS_FLOW, bool ALL_IN, typename T>
+__device__ __forceinline__ void gather_slab(const T* __restrict__ c2, const Params& P, float4* __restrict__ sB_slot,
+                                            const int4* __restrict__ scratch, int lane) {
+  // LPP lanes per pixel, KQ channel chunks per lane; NIT items are loaded before any is used.
+  // ALL_IN: every pixel of the slab lies inside the image (warp-uniform), so there is no per-item predicate.
+  constexpr int PPI = 32 / G::LPP;               // pixels per warp iteration
+  constexpr int NITEMS = G::NPIX * G::KQ / PPI;  // per-lane items of the slab
+  constexpr int NIT = NITEMS % 4 == 0 ? 4 : 2;
+  static_assert(NITEMS % NIT == 0, "gather batching");
+  constexpr int CELT = G::KV * 4;                // channels (compile-time: corner offsets become immediates)
+  const int sub = lane / G::LPP, kvl = lane % G::LPP;
+  const size_t rowstride = (size_t)P.W * CELT;
+#pragma unroll 1
+  for (int i0 = 0; i0 < NITEMS; i0 += NIT) {
+    float4 tl[NIT], tr[NIT], bl[NIT], br[NIT];
+    int4 cd[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int item = i0 + it;  // item -> (pixel group, kv chunk): the chunks of a pixel are adjacent items
+      const int e = (item / G::KQ) * PPI + sub, q = item % G::KQ;
+      cd[it] = scratch[e];
+      const int kv = kvl + q * G::LPP;
+      cd[it].w += kv * G::B_PLANE;
+      const bool ok = ALL_IN || cd[it].x >= 0;
+      const T* base = c2 + (size_t)(ok ? cd[it].x : 0) * CELT + 4 * kv;
+      tl[it] = ld4(base);
+      if (HAS_FLOW) {
+        tr[it] = ld4(base + CELT);
+        bl[it] = ld4(base + rowstride);
+        br[it] = ld4(base + rowstride + CELT);
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      float4 v = tl[it];
+      if (HAS_FLOW)
+        v = round4<T>(bilerp4_fast(tl[it], tr[it], bl[it], br[it], __int_as_float(cd[it].y), __int_as_float(cd[it].z)));
+      if (!ALL_IN && cd[it].x < 0) v = make_float4(0.f, 0.f, 0.f, 0.f);
+      sB_slot[cd[it].w] = v;
+    }
+  }
+}
+
 template <typename G, bool HAS_FLOW, typename T, typename TF>
 __device__ __forceinline__ void produce_slab(const T* __restrict__ c2, const TF* __restrict__ flow, const Params& P,
                                              const Seg& sg, int m, float4* __restrict__ sB_slot,
                                              int4* __restrict__ scratch, int lane) {
   __syncwarp();  // every lane is done reading the previous slab's scratch
   // phase 1: per pixel {top-left corner index or -1, ax, ay, smem offset} -> per-warp scratch
+  bool all_in = true;
 #pragma unroll
   for (int e0 = 0; e0 < G::NPIX; e0 += 32) {
     const int e = e0 + lane;
@@ -197,49 +241,15 @@ __device__ __forceinline__ void produce_slab(const T* __restrict__ c2, const TF*
         } else {
           cd.x = (sg.b * P.H + y) * P.W + x;
         }
+      } else {
+        all_in = false;
       }
       scratch[e] = cd;
     }
   }
-  __syncwarp();
-  // phase 2: LPP lanes per pixel, KQ channel chunks per lane; NIT items are loaded before any is used
-  constexpr int PPI = 32 / G::LPP;               // pixels per warp iteration
-  constexpr int NITEMS = G::NPIX * G::KQ / PPI;  // per-lane items of the slab
-  constexpr int NIT = NITEMS % 4 == 0 ? 4 : 2;
-  static_assert(NITEMS % NIT == 0, "gather batching");
-  const int sub = lane / G::LPP, kvl = lane % G::LPP;
-  const size_t rowstride = (size_t)P.W * P.C;
-#pragma unroll 1
-  for (int i0 = 0; i0 < NITEMS; i0 += NIT) {
-    float4 tl[NIT], tr[NIT], bl[NIT], br[NIT];
-    int4 cd[NIT];
-#pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-      const int item = i0 + it;  // item -> (pixel group, kv chunk): the chunks of a pixel are adjacent items
-      const int e = (item / G::KQ) * PPI + sub, q = item % G::KQ;
-      cd[it] = scratch[e];
-      const int kv = kvl + q * G::LPP;
-      cd[it].w += kv * G::B_PLANE;
-      tl[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (HAS_FLOW) { tr[it] = tl[it]; bl[it] = tl[it]; br[it] = tl[it]; }
-      if (cd[it].x >= 0) {
-        const T* base = c2 + (size_t)cd[it].x * P.C + 4 * kv;
-        tl[it] = ld4(base);
-        if (HAS_FLOW) {
-          tr[it] = ld4(base + P.C);
-          bl[it] = ld4(base + rowstride);
-          br[it] = ld4(base + rowstride + P.C);
-        }
-      }
-    }
-#pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-      float4 v = tl[it];
-      if (HAS_FLOW)
-        v = round4<T>(bilerp4_fast(tl[it], tr[it], bl[it], br[it], __int_as_float(cd[it].y), __int_as_float(cd[it].z)));
-      sB_slot[cd[it].w] = v;
-    }
-  }
+  all_in = __all_sync(0xffffffffu, all_in);  // also orders the scratch writes before the reads below
+  if (all_in) gather_slab<G, HAS_FLOW, true, T>(c2, P, sB_slot, scratch, lane);
+  else        gather_slab<G, HAS_FLOW, false, T>(c2, P, sB_slot, scratch, lane);
 }
 
 // ---- per-lane correlation: 1 row x 8 pixels x 9 dx against ONE warped row, kv in [kv0, kv1) ------------

@@ -26,6 +26,7 @@ std::atomic<int> g_fwd_impl{0};
 std::atomic<int> g_stream_ctas{0};
 std::atomic<int> g_stream_pf{4};
 std::atomic<int> g_stream_dbg{0};
+std::atomic<int> g_overlap{1};
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -356,6 +357,10 @@ int pwc_set_option(const char* key, int value) {
     g_stream_pf.store(value);
     return PWC_OK;
   }
+  if (!strcmp(key, "overlap_levels")) {
+    g_overlap.store(value);
+    return PWC_OK;
+  }
   if (!strcmp(key, "stream_debug")) {  // timing experiments only; results are wrong when non-zero
     g_stream_dbg.store(value);
     return PWC_OK;
@@ -368,6 +373,7 @@ int pwc_get_option(const char* key, int* value) {
   if (!strcmp(key, "stream_ctas")) { *value = g_stream_ctas.load(); return PWC_OK; }
   if (!strcmp(key, "stream_prefetch")) { *value = g_stream_pf.load(); return PWC_OK; }
   if (!strcmp(key, "stream_debug")) { *value = g_stream_dbg.load(); return PWC_OK; }
+  if (!strcmp(key, "overlap_levels")) { *value = g_overlap.load(); return PWC_OK; }
   return fail(PWC_ERR_BAD_ARG, "unknown option '%s'", key);
 }
 
@@ -387,15 +393,66 @@ int pwc_warp_cost_volume_fwd(const void* c1, const void* c2, const void* flow, f
   return fwd_entry(c1, c2, flow, flow_scale, out, B, H, W, C, r, dtype, flow_dtype, out_pixel_stride, cuda_stream);
 }
 
+// The levels of one pass are independent operator calls (their inputs are given), and the short levels are
+// latency-bound with far fewer CTAs than SMs, so they are forked onto side streams and joined at the end:
+// cuda_stream still sees "all levels done" as one unit of stream-ordered work.
+namespace {
+struct SideStreams {
+  cudaStream_t s[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[3] = {nullptr, nullptr, nullptr};
+  bool ok = false;
+};
+SideStreams* side_streams_for_device() {
+  static thread_local SideStreams per_dev[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideStreams& S = per_dev[dev];
+  if (!S.ok) {
+    for (int i = 0; i < 3; ++i) {
+      if (cudaStreamCreateWithFlags(&S.s[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&S.join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    if (cudaEventCreateWithFlags(&S.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    S.ok = true;
+  }
+  return &S;
+}
+}  // namespace
+
 int pwc_pyramid_fwd(const pwc_level_t* levels, int n_levels, int B, int r, int dtype, int flow_dtype,
                     void* cuda_stream) {
   if (n_levels < 0 || (n_levels > 0 && !levels)) return fail(PWC_ERR_BAD_ARG, "bad level list");
+  cudaStream_t main_st = (cudaStream_t)cuda_stream;
+  SideStreams* S = (n_levels > 1 && g_overlap.load()) ? side_streams_for_device() : nullptr;
+  int n_side = 0;
+  bool used[3] = {false, false, false};
+  // tall levels first, in order, on the caller's stream (their persistent kernels want every SM) ...
   for (int i = 0; i < n_levels; ++i) {
     const pwc_level_t& L = levels[i];
+    if (S && L.H < 40) continue;
     int rc = fwd_entry(L.c1, L.c2, L.flow, L.flow_scale, L.out, B, L.H, L.W, L.C, r, dtype, flow_dtype,
-                       L.out_pixel_stride, cuda_stream);
+                       L.out_pixel_stride, main_st);
     if (rc) return rc;
   }
+  // ... then the short levels side by side (few CTAs each; same H threshold as the kernel choice)
+  if (S) {
+    PWC_CUDA(cudaEventRecord(S->fork, main_st));
+    for (int i = 0; i < n_levels; ++i) {
+      const pwc_level_t& L = levels[i];
+      if (L.H >= 40) continue;
+      const int k = n_side++ % 3;
+      if (!used[k]) { PWC_CUDA(cudaStreamWaitEvent(S->s[k], S->fork, 0)); used[k] = true; }
+      int rc = fwd_entry(L.c1, L.c2, L.flow, L.flow_scale, L.out, B, L.H, L.W, L.C, r, dtype, flow_dtype,
+                         L.out_pixel_stride, S->s[k]);
+      if (rc) return rc;
+    }
+  }
+  if (S)
+    for (int k = 0; k < 3; ++k)
+      if (used[k]) {
+        PWC_CUDA(cudaEventRecord(S->join[k], S->s[k]));
+        PWC_CUDA(cudaStreamWaitEvent(main_st, S->join[k], 0));
+      }
   return PWC_OK;
 }
 
