@@ -137,8 +137,7 @@ template <typename G, typename T>
 __device__ __forceinline__ void produce_pair(const T* __restrict__ c1, const Params& P, const Seg& sg, int k,
                                              float4* __restrict__ sA_slot, int lane, float inv_c) {
   constexpr int ITEMS = 2 * G::TW * G::KV / 32;  // per lane
-  constexpr int BATCH = 4;
-  static_assert(ITEMS % BATCH == 0, "pair batching");
+  constexpr int BATCH = ITEMS;                   // one batch: all loads in flight together (one latency exposure)
 #pragma unroll 1
   for (int b0 = 0; b0 < ITEMS; b0 += BATCH) {
     float4 v[BATCH];
@@ -225,24 +224,40 @@ __device__ __forceinline__ void produce_slab(const T* __restrict__ c2, const TF*
                                              const Seg& sg, int m, float4* __restrict__ sB_slot,
                                              int4* __restrict__ scratch, int lane) {
   __syncwarp();  // every lane is done reading the previous slab's scratch
-  // phase 1: per pixel {top-left corner index or -1, ax, ay, smem offset} -> per-warp scratch
+  // phase 1: per pixel {top-left corner index or -1, ax, ay, smem offset} -> per-warp scratch.
+  // All flow loads are issued before any is used (one latency exposure for the whole slab).
+  constexpr int NP1 = (G::NPIX + 31) / 32;
+  TF f0[NP1], f1[NP1];
+  bool inside[NP1];
   bool all_in = true;
 #pragma unroll
-  for (int e0 = 0; e0 < G::NPIX; e0 += 32) {
-    const int e = e0 + lane;
+  for (int i = 0; i < NP1; ++i) {
+    const int e = i * 32 + lane;
+    const int bsel = e / G::BU, u = e - bsel * G::BU;
+    const int y = 2 * m - 1 + bsel, x = sg.x0 - R + u;
+    inside[i] = e < G::NPIX && y >= 0 && y < P.H && x >= 0 && x < P.W;
+    if (e < G::NPIX && !inside[i]) all_in = false;
+    f0[i] = f1[i] = TF(0.0f);
+    if (HAS_FLOW && inside[i]) {
+      const size_t p = ((size_t)sg.b * P.H + y) * P.W + x;
+      f0[i] = flow[2 * p];
+      f1[i] = flow[2 * p + 1];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NP1; ++i) {
+    const int e = i * 32 + lane;
     if (e < G::NPIX) {
       const int bsel = e / G::BU, u = e - bsel * G::BU;
       const int y = 2 * m - 1 + bsel, x = sg.x0 - R + u;
       int4 cd = make_int4(-1, 0, 0, (u + u / PX) * 2 + bsel);
-      if (y >= 0 && y < P.H && x >= 0 && x < P.W) {
+      if (inside[i]) {
         if (HAS_FLOW) {
-          const SampleCoord s = sample_coord<T, TF>(flow, P.flow_scale, sg.b, y, x, P.H, P.W);
+          const SampleCoord s = sample_coord_v<T, TF>(f0[i], f1[i], P.flow_scale, sg.b, y, x, P.H, P.W);
           cd.x = s.pix; cd.y = __float_as_int(s.ax); cd.z = __float_as_int(s.ay);
         } else {
           cd.x = (sg.b * P.H + y) * P.W + x;
         }
-      } else {
-        all_in = false;
       }
       scratch[e] = cd;
     }

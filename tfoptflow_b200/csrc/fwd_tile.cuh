@@ -39,7 +39,10 @@ struct Cfg {
 };
 
 template <int R, typename T, typename TF>
-__global__ void __maxnreg__(112)
+#ifndef PWC_TILE_MAXNREG
+#define PWC_TILE_MAXNREG 112
+#endif
+__global__ void __maxnreg__(PWC_TILE_MAXNREG)
 fwd_tile_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* __restrict__ flow,
                 float flow_scale, T* __restrict__ out, int B, int H, int W, int C,
                 int64_t out_pixel_stride, int tiles_x, int tiles_y) {
@@ -88,34 +91,69 @@ fwd_tile_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* __
 
   for (int c0 = 0; c0 < C; c0 += K::CK) {
     __syncthreads();  // coords visible / previous chunk consumed
-    // ---- phase 1a: c1 tile ----
-    for (int i = tid; i < TH * TW * KV; i += K::NTHREADS) {
-      const int kv = i % KV, p = i / KV;
-      const int row = p / TW, col = p - row * TW;
-      const int y = y0 + row, x = x0 + col, c = c0 + 4 * kv;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (y < H && x < W && c < C) v = ld4(c1 + (((size_t)b * H + y) * W + x) * C + c);
-      sA[kv * K::A_PLANE + row * K::A_RS + col + col / PX] = v;
-    }
-    // ---- phase 1b: warped c2 tile + halo ----
-    for (int i = tid; i < K::COORD_N * KV; i += K::NTHREADS) {
-      const int kv = i % KV, p = i / KV;
-      const int4 cd = sCoord[p];
-      const int c = c0 + 4 * kv;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (cd.w != 0 && c < C) {
-        if (cd.w == 2) {
-          v = ld4(c2 + (size_t)cd.x * C + c);
-        } else {
-          SampleCoord s;
-          s.pix = cd.x;
-          s.ax = __int_as_float(cd.y);
-          s.ay = __int_as_float(cd.z);
-          v = sample4<T>(c2, s, W, C, c);
+    // ---- phase 1a: c1 tile (FA loads in flight per thread) ----
+    {
+      constexpr int NA = TH * TW * KV, FA = 4;
+#pragma unroll 1
+      for (int i0 = tid; i0 < NA; i0 += FA * K::NTHREADS) {
+        float4 v[FA];
+#pragma unroll
+        for (int j = 0; j < FA; ++j) {
+          const int i = i0 + j * K::NTHREADS;
+          const int kv = i % KV, p = i / KV;
+          const int row = p / TW, col = p - row * TW;
+          const int y = y0 + row, x = x0 + col, c = c0 + 4 * kv;
+          v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < NA && y < H && x < W && c < C) v[j] = ld4(c1 + (((size_t)b * H + y) * W + x) * C + c);
+        }
+#pragma unroll
+        for (int j = 0; j < FA; ++j) {
+          const int i = i0 + j * K::NTHREADS;
+          const int kv = i % KV, p = i / KV;
+          const int row = p / TW, col = p - row * TW;
+          if (i < NA) sA[kv * K::A_PLANE + row * K::A_RS + col + col / PX] = v[j];
         }
       }
-      const int rb = p / K::BW, u = p - rb * K::BW;
-      sB[kv * K::B_PLANE + rb * K::B_RS + u + u / PX] = v;
+    }
+    // ---- phase 1b: warped c2 tile + halo (FB items = 4*FB corner loads in flight per thread) ----
+    {
+      constexpr int NB = K::COORD_N * KV, FB = 3;
+      const size_t rowstride = (size_t)W * C;
+#pragma unroll 1
+      for (int i0 = tid; i0 < NB; i0 += FB * K::NTHREADS) {
+        float4 tl[FB], tr[FB], bl[FB], br[FB];
+        int4 cd[FB];
+#pragma unroll
+        for (int j = 0; j < FB; ++j) {
+          const int i = i0 + j * K::NTHREADS;
+          const int kv = i % KV, p = i / KV;
+          cd[j] = make_int4(0, 0, 0, 0);
+          if (i < NB) cd[j] = sCoord[p];
+          const int c = c0 + 4 * kv;
+          if (c >= C) cd[j].w = 0;
+          tl[j] = tr[j] = bl[j] = br[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (cd[j].w != 0) {
+            const T* base = c2 + (size_t)cd[j].x * C + c;
+            tl[j] = ld4(base);
+            if (cd[j].w == 1) {
+              tr[j] = ld4(base + C);
+              bl[j] = ld4(base + rowstride);
+              br[j] = ld4(base + rowstride + C);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < FB; ++j) {
+          const int i = i0 + j * K::NTHREADS;
+          if (i >= NB) continue;
+          const int kv = i % KV, p = i / KV;
+          float4 v = tl[j];
+          if (cd[j].w == 1)
+            v = round4<T>(bilerp4(tl[j], tr[j], bl[j], br[j], __int_as_float(cd[j].y), __int_as_float(cd[j].z)));
+          const int rb = p / K::BW, u = p - rb * K::BW;
+          sB[kv * K::B_PLANE + rb * K::B_RS + u + u / PX] = v;
+        }
+      }
     }
     __syncthreads();
     // ---- phase 2: register-tiled correlation ----

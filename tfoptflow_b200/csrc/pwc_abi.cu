@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <type_traits>
@@ -139,6 +140,13 @@ int fwd_typed(const void* c1, const void* c2, const void* flow, float flow_scale
     PWC_CUDA(cudaGetDevice(&devid));
     if (!((attr_set.load() >> devid) & 1)) {
       PWC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
+      // two co-resident CTAs per SM (93 KB each) hide each other's fill/compute phases
+      PWC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      if (getenv("PWC_DEBUG_OCC")) {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, K::NTHREADS, K::SMEM_BYTES);
+        fprintf(stderr, "[pwc] tile kernel occupancy: %d CTAs/SM\n", nb);
+      }
       attr_set.fetch_or(uint64_t(1) << devid);
     }
     const int tiles_x = (W + K::TW - 1) / K::TW, tiles_y = (H + K::TH - 1) / K::TH;
