@@ -104,6 +104,10 @@ int pwc_host_ctx_destroy(pwc_host_ctx* ctx);
 int pwc_pyramid_fwd_host(pwc_host_ctx* ctx, const pwc_level_t* host_levels, int n_levels,
                          int B, int r, int dtype, int flow_dtype);
 
+/* Diagnostics: copies the streaming kernel's event trace (CTA 0; recorded when option stream_debug has bit 16
+ * set) into dst_host; returns the number of bytes copied or a negative error.  Synchronises the device. */
+int pwc_debug_read_trace(void* dst_host, int max_bytes);
+
 /* ---- backward ----------------------------------------------------------------------- */
 
 /* Scratch needed by the *_bwd entry points for this problem (bytes, 256-aligned). */

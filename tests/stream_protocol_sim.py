@@ -43,8 +43,10 @@ def lane_tasks(sg, tl, NXG):
     if not is_edge and GS * g + ((rr * NH) >> 3) >= sg["nslab"]:
         return out
     for lane in range(32):
-        lo, xg, hi = lane & 1, (lane >> 1) % NXG, lane // (2 * NXG)
+        lo = lane & 1
         if not is_edge:
+            # full tasks: (warped row, c1 row, x-group) so that every aligned group of 4 lanes shares operands
+            hi, xg = (lane >> 1) % NH, lane // (2 * NH)
             c = rr * NH + hi
             l = GS * g + (c >> 3)
             r8 = c & 7
@@ -54,6 +56,7 @@ def lane_tasks(sg, tl, NXG):
             arrive_a = lo == 0 and xg == 0 and sub == 0
             kfrac = 1
         else:
+            xg, hi = (lane >> 1) % NXG, lane // (2 * NXG)
             ms, part = divmod(hi, KP)
             l = GS * g + ms
             k = sg["p0"] - 2 + l + (2 if lo == 0 else -3)

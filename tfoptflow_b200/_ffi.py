@@ -36,6 +36,7 @@ SIGNATURES = {
     "pwc_launch_count": (ctypes.c_uint64, []),
     "pwc_set_option": (_i, [ctypes.c_char_p, _i]),
     "pwc_get_option": (_i, [ctypes.c_char_p, ctypes.POINTER(_i)]),
+    "pwc_debug_read_trace": (_i, [_vp, _i]),
     "pwc_cost_volume_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i64, _vp]),
     "pwc_dense_image_warp_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "pwc_warp_cost_volume_fwd": (_i, [_vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _i, _i, _i64, _vp]),

@@ -4,31 +4,44 @@
 // TW = 8 * NXG pixels (32 / 16 / 8 for C <= 32 / 64 / >= 96, so that all channels of the rows in flight fit in
 // shared memory); every CTA owns a contiguous range of (strip, row-pair) work and marches down it.
 //   * NPW producer warps evaluate the bilinear warp of c2 (8 lanes per pixel read whole 128-byte lines of every
-//     corner) and stream the *warped* rows ("slabs" = warped rows 2m-1, 2m), plus the matching c1 row pairs, into
-//     two shared-memory rings guarded by mbarriers.  Warped features never reach HBM.  Each producer warp owns every
-//     NPW-th slab, so NPW gathers are in flight.
+//     corner, 4-tap weighted sum in packed FFMA2) and stream the *warped* rows ("slabs" = warped rows 2m-1, 2m) into
+//     a shared-memory ring guarded by mbarriers.  The warped features never reach HBM; the 1/C of the channel mean is
+//     folded into the bilinear weights.  The matching c1 row pairs arrive through TMA bulk copies
+//     (cp.async.bulk -> mbarrier complete_tx; no registers, no issue slots) for fp32, by LDG/STS for 16-bit inputs.
+//     Each producer warp owns every NPW-th slab, so NPW gathers are in flight.
 //   * NCW compute warps pull tasks in order.  Every task is 32 independent lane-tasks: one c1 row against one
-//     warped row, 8 pixels x 9 dx, 72 accumulators, every LDS.128 operand feeding up to 36 FMAs.  Lanes are laid out
-//     (warped row, x-group, c1 row) so that c1 operands are shared by the two warped rows of a slab and warped
-//     operands by all c1 rows (LDS broadcast).  A slab sees c1 rows 2m-4 .. 2m+3 (full tasks F); the two remaining
-//     displacements (row 2m+4 with dy=-4, row 2m-5 with dy=+4) are done by one edge task E per 4 slabs, with the
-//     channel range split over 4/NXG lanes and reduced by shuffles.
+//     warped row, 8 pixels x 9 dx.  Accumulators are channel PAIRS (72 x f32x2) so that the inner loop is packed
+//     FFMA2: one issue slot per two FMAs, which leaves issue bandwidth for the LDS.128 operand stream, the producers
+//     and the epilogue.  Lanes are laid out (warped row, c1 row, x-group): every aligned group of 4 lanes sees at most
+//     2 distinct c1 operands and 2 distinct warped operands, the pattern the LDS crossbar serves in 2 cycles per
+//     LDS.128 instead of 4 (scripts/ubench/lds_pattern.cu).  A slab sees c1 rows 2m-4 .. 2m+3 (full tasks F); the two
+//     remaining displacements (row 2m+4 with dy=-4, row 2m-5 with dy=+4) are done by one edge task E per 4 slabs,
+//     with the channel range split over 4/NXG lanes and reduced by shuffles.
 //   * Results go through a per-warp transposition buffer: each store instruction writes runs of 9 / 18 channels.
+// Shared-memory layout is pixel-major ([pixel][channel], what TMA delivers) with 16-byte pads chosen so that the
+// operands of one LDS land in distinct bank groups: row stride = 1, pair slot = 2, x-group = 4 (c1) / 2 (warped)
+// mod 8 float4.
 // Zero padding is applied after warping (core_costvol.py:27); the warp clamps (core_warp.py:101-104).
 // The ring protocol (two alternating mbarrier sets per slot) is modelled in tests/stream_protocol_sim.py.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 namespace pwc {
 namespace stream {
 
+typedef unsigned long long u64;
+
 constexpr int R = 4, ND = 9, D = 81, PX = 8;
-constexpr int NCW = 8;   // compute warps
-constexpr int NPW = 4;   // producer warps
+constexpr int NCW = 8;   // compute warps (two warpgroups)
+constexpr int NPW = 4;   // producer warps (one warpgroup)
 constexpr int NTHREADS = 32 * (NCW + NPW);
+constexpr int REGS_COMPUTE = 200, REGS_PRODUCER = 104;  // setmaxnreg moves registers inside the CTA allocation: 2*200 + 104 = 3*168
 constexpr int MAXSEG = 8;
 constexpr int GS = 4;    // slabs per task group (one edge task per group)
 constexpr size_t SMEM_LIMIT = 232448;
+
+constexpr int pad_to(int v, int r) { return v + ((r - v % 8) + 8) % 8; }  // smallest v' >= v with v' % 8 == r
 
 template <int KV_, int NXG_>
 struct Geo {
@@ -36,31 +49,37 @@ struct Geo {
   static constexpr int TW = PX * NXG;                 // strip width
   static constexpr int BU = TW + 2 * R;               // warped pixels per row (with halo)
   static constexpr int NPIX = 2 * BU;                 // pixels per slab
-  static constexpr int B_USLOTS = 9 * NXG + 8;        // slot(u) = u + u/8
-  static constexpr int A_ROWSLOTS = 9 * NXG;
-  static constexpr int B_PLANE = B_USLOTS * 2 + 1;    // float4 per kv plane, odd => kv-strided stores conflict-free
-  static constexpr int A_PLANE = A_ROWSLOTS * 2 + 1;
-  static constexpr int BSLOT = KV * B_PLANE;
-  static constexpr int ASLOT = KV * A_PLANE + 1;      // +1: consecutive pair slots start in different banks
+  // float4 units.  c1 pair slot: [sub(2)][xg][p(8)][kv] ; warped slab slot: [bsel(2)][u(BU)][kv], 2 pads per 8 pixels
+  static constexpr int AXG = 8 * KV + 4;
+  static constexpr int AROW = pad_to(NXG * AXG, 1);
+  static constexpr int ASLOT = 2 * AROW;
+  static constexpr int BXPAD = 2;
+  static constexpr int BXG = 8 * KV + BXPAD;
+  static constexpr int BROW = pad_to(BU * KV + (BU / 8) * BXPAD, 1);
+  static constexpr int BSLOT = 2 * BROW;
+  static_assert(AXG % 8 == 4 && AROW % 8 == 1 && ASLOT % 8 == 2 && BROW % 8 == 1, "bank-group strides");
   static constexpr int NH = 16 / NXG;                 // c1 rows (hi values) per full task
   static constexpr int NF = 8 * GS / NH;              // full tasks per group: 8 / 4 / 2
   static constexpr int TPG = NF + 1;                  // + one edge task
   static constexpr int KP = 4 / NXG;                  // channel split of the edge task
+  static constexpr int KU = (KV / KP) % 8 == 0 ? 8 : ((KV / KP) % 6 == 0 ? 6 : 4);  // unroll of the channel loop
   static constexpr int EMPTYB_COUNT = (NXG == 4 ? 2 : 1) + 1;
   static constexpr int LPP = KV >= 8 ? 8 : KV;        // producer lanes per pixel
   static constexpr int KQ = KV / LPP;                 // kv chunks per lane
-  static constexpr int NSLAB = KV <= 8 ? 7 : (KV == 24 ? 7 : 6);
-  static constexpr int NAP = KV <= 8 ? 12 : (KV == 32 ? 10 : 12);
+  static constexpr int NSLAB = KV == 32 ? 6 : (KV == 16 ? 6 : (KV == 8 ? 8 : 7));
+  static constexpr int NAP = KV == 32 ? 10 : 12;     // even: the wrap-around keeps consecutive pairs 2 bank groups apart
   static constexpr int STAGE_WORDS = 640;             // per compute warp (2 x 320, double buffered)
   static constexpr size_t OFF_B = 0;
   static constexpr size_t OFF_A = OFF_B + (size_t)NSLAB * BSLOT * 16;
   static constexpr size_t OFF_STAGE = OFF_A + (size_t)NAP * ASLOT * 16;
-  static constexpr size_t OFF_SCRATCH = OFF_STAGE + (size_t)NCW * STAGE_WORDS * 4;
-  static constexpr size_t OFF_BAR = OFF_SCRATCH + (size_t)NPW * NPIX * 16;
+  static constexpr size_t OFF_SCRW = OFF_STAGE + (size_t)NCW * STAGE_WORDS * 4;   // float4 weights per pixel
+  static constexpr size_t OFF_SCRP = OFF_SCRW + (size_t)NPW * NPIX * 16;          // int2 {corner pixel, smem offset}
+  static constexpr size_t OFF_BAR = OFF_SCRP + (size_t)NPW * NPIX * 8;
   static constexpr size_t OFF_SEG = OFF_BAR + (size_t)(4 * NSLAB + 4 * NAP) * 8;
-  static constexpr size_t SMEM_BYTES = OFF_SEG + MAXSEG * 32 + 64;
+  static constexpr size_t OFF_ACNT = OFF_SEG + MAXSEG * 32 + 64;                  // consumer arrivals per c1 pair slot
+  static constexpr size_t SMEM_BYTES = OFF_ACNT + NAP * 4;
   static_assert(SMEM_BYTES <= SMEM_LIMIT, "shared memory budget");
-  static_assert(KV % LPP == 0 && KV % KP == 0, "channel split");
+  static_assert(KV % LPP == 0 && KV % KP == 0 && NAP % 2 == 0, "channel split / ring");
 };
 
 struct Seg {
@@ -77,16 +96,28 @@ struct Params {
   int nstrip_x;     // ceil(W / TW)
   long long Q;      // total (strip, pair) units
   int pf_dist;      // L2 prefetch distance in slabs (0 = off)
-  int dbg;          // timing experiments only: 1 = skip correlate, 2 = skip gathers, 4 = skip stores
+  int dbg;          // timing experiments only: 1 = skip correlate, 2 = skip gathers, 4 = skip stores; 8 = c1 by LDG
 };
 
-// ---- mbarrier helpers (generic-proxy producers/consumers only) ---------------------------
+// ---- event trace (diagnostics, stream_debug bit 16): CTA 0 records (clock << 16 | code << 12 | value) per warp ----
+constexpr int TRACE_LEN = 512;
+__device__ unsigned long long g_trace[NCW + NPW][TRACE_LEN];
+#define PWC_TR(code, val)                                                                              \
+  do {                                                                                                 \
+    if ((P.dbg & 16) && blockIdx.x == 0 && lane == 0 && tr_n < TRACE_LEN)                              \
+      g_trace[warp][tr_n++] = ((unsigned long long)clock64() << 16) | ((code) << 12) | ((val) & 0xfff); \
+  } while (0)
+
+// ---- mbarrier / TMA helpers ----------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
@@ -101,12 +132,45 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
-
-// ---- producer ------------------------------------------------------------------------------
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
+// ---- packed fp32 (sm_100 FFMA2 / FMUL2) ----------------------------------------------------
+__device__ __forceinline__ void ffma2(u64& d, u64 a, u64 b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+// scalar weight x packed pair: ptxas folds the {w, w} pair into the scalar-broadcast operand form
+__device__ __forceinline__ void ffma2s(u64& d, float w, u64 b) {
+  u64 ww;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(ww), "l"(b));
+}
+__device__ __forceinline__ u64 fmul2s(float w, u64 b) {
+  u64 ww, r;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(ww), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 pack2(float x, float y) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+  return r;
+}
+__device__ __forceinline__ float2 unpack2(u64 v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+
+// ---- producer ------------------------------------------------------------------------------
 // pull the leading edge of a future slab (2 rows of c2, c1 and flow) towards L2
 template <typename G, typename T, typename TF>
 __device__ __forceinline__ void prefetch_rows(const T* c1, const T* c2, const TF* flow, const Params& P, const Seg& sg,
@@ -132,167 +196,225 @@ __device__ __forceinline__ void prefetch_rows(const T* c1, const T* c2, const TF
   if (hi > lo) bulk_prefetch_l2(reinterpret_cast<const void*>(lo), (uint32_t)(hi - lo));
 }
 
-// c1 rows 2k, 2k+1 of the strip, scaled by 1/C (the channel mean is folded into c1)
+// c1 rows 2k, 2k+1 of the strip by TMA: one bulk copy per (row, 8-pixel group), i.e. 1 KB at C = 32
+template <typename G>
+__device__ __forceinline__ void produce_pair_tma(const float* __restrict__ c1, const Params& P, const Seg& sg, int k,
+                                                 float4* __restrict__ sA_slot, uint64_t* bar, int lane) {
+  if (lane == 0) {
+    const int rows = min(2, P.H - 2 * k), px = min(G::TW, P.W - sg.x0);
+    mbar_arrive_expect_tx(bar, (uint32_t)(rows * px * P.C * 4));
+  }
+  __syncwarp();
+  if (lane < 2 * G::NXG) {
+    const int row = lane / G::NXG, xg = lane % G::NXG;
+    const int y = 2 * k + row, x = sg.x0 + PX * xg;
+    if (y < P.H && x < P.W) {
+      const int npx = min(PX, P.W - x);
+      bulk_g2s(sA_slot + row * G::AROW + xg * G::AXG, c1 + (((size_t)sg.b * P.H + y) * P.W + x) * P.C,
+               (uint32_t)(npx * P.C * 4), bar);
+    }
+  }
+}
+
+// The same by a single lane, for global pair index `ag` (segment looked up in the table): used by the consumer that
+// frees a slot to refill it at once (credit return: no producer ever waits for c1 space).
+template <typename G>
+__device__ __forceinline__ void refill_pair_tma(const float* __restrict__ c1, const Params& P, const Seg* segs, int nseg,
+                                                int ag, float4* __restrict__ sA, uint64_t* fullA) {
+  int si = 0;
+  while (si + 1 < nseg && segs[si + 1].a0 <= ag) ++si;
+  const int b = segs[si].b, x0 = segs[si].x0, k = segs[si].p0 + (ag - segs[si].a0);
+  uint64_t* bar = &fullA[ag % (2 * G::NAP)];
+  float4* slot = sA + (size_t)(ag % G::NAP) * G::ASLOT;
+  const int rows = min(2, P.H - 2 * k), px = min(G::TW, P.W - x0);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // consumers' generic reads of the slot come first
+  mbar_arrive_expect_tx(bar, (uint32_t)(rows * px * P.C * 4));
+  for (int row = 0; row < rows; ++row)
+    for (int xg = 0; xg * PX < px; ++xg) {
+      const int x = x0 + PX * xg, npx = min(PX, P.W - x);
+      bulk_g2s(slot + row * G::AROW + xg * G::AXG, c1 + (((size_t)b * P.H + 2 * k + row) * P.W + x) * P.C,
+               (uint32_t)(npx * P.C * 4), bar);
+    }
+}
+
+// c1 rows 2k, 2k+1 of the strip by LDG / STS (16-bit inputs are widened to fp32 on the way).
+// All loads are issued before any use (one latency exposure).
 template <typename G, typename T>
 __device__ __forceinline__ void produce_pair(const T* __restrict__ c1, const Params& P, const Seg& sg, int k,
-                                             float4* __restrict__ sA_slot, int lane, float inv_c) {
+                                             float4* __restrict__ sA_slot, int lane) {
   constexpr int ITEMS = 2 * G::TW * G::KV / 32;  // per lane
-  constexpr int BATCH = ITEMS;                   // one batch: all loads in flight together (one latency exposure)
-#pragma unroll 1
-  for (int b0 = 0; b0 < ITEMS; b0 += BATCH) {
-    float4 v[BATCH];
+  float4 v[ITEMS];
 #pragma unroll
-    for (int it = 0; it < BATCH; ++it) {
-      const int id = (b0 + it) * 32 + lane;
-      const int kv = id % G::KV, pxl = id / G::KV;
-      const int row = pxl / G::TW, col = pxl - row * G::TW;
-      const int y = 2 * k + row, x = sg.x0 + col;
-      v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (y < P.H && x < P.W) v[it] = ld4(c1 + (((size_t)sg.b * P.H + y) * P.W + x) * P.C + 4 * kv);
-    }
+  for (int it = 0; it < ITEMS; ++it) {
+    const int id = it * 32 + lane;
+    const int kv = id % G::KV, pxl = id / G::KV;
+    const int row = pxl / G::TW, col = pxl - row * G::TW;
+    const int y = 2 * k + row, x = sg.x0 + col;
+    v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (y < P.H && x < P.W) v[it] = ld4(c1 + (((size_t)sg.b * P.H + y) * P.W + x) * P.C + 4 * kv);
+  }
 #pragma unroll
-    for (int it = 0; it < BATCH; ++it) {
-      const int id = (b0 + it) * 32 + lane;
-      const int kv = id % G::KV, pxl = id / G::KV;
-      const int row = pxl / G::TW, col = pxl - row * G::TW;
-      float4 w = v[it];
-      w.x *= inv_c; w.y *= inv_c; w.z *= inv_c; w.w *= inv_c;
-      sA_slot[kv * G::A_PLANE + row * G::A_ROWSLOTS + col + col / PX] = w;
-    }
+  for (int it = 0; it < ITEMS; ++it) {
+    const int id = it * 32 + lane;
+    const int kv = id % G::KV, pxl = id / G::KV;
+    const int row = pxl / G::TW, col = pxl - row * G::TW;
+    sA_slot[row * G::AROW + (col / PX) * G::AXG + (col % PX) * G::KV + kv] = v[it];
   }
 }
 
-// bilinear blend with FMA lerps (the fused path is checked against the oracle with a tolerance; the standalone
-// dense_image_warp kernel keeps the reference's exact op order)
-__device__ __forceinline__ float4 bilerp4_fast(const float4& tl, const float4& tr, const float4& bl, const float4& br,
-                                               float ax, float ay) {
-  float4 o;
-  float t, b;
-  t = fmaf(ax, tr.x - tl.x, tl.x); b = fmaf(ax, br.x - bl.x, bl.x); o.x = fmaf(ay, b - t, t);
-  t = fmaf(ax, tr.y - tl.y, tl.y); b = fmaf(ax, br.y - bl.y, bl.y); o.y = fmaf(ay, b - t, t);
-  t = fmaf(ax, tr.z - tl.z, tl.z); b = fmaf(ax, br.z - bl.z, bl.z); o.z = fmaf(ay, b - t, t);
-  t = fmaf(ax, tr.w - tl.w, tl.w); b = fmaf(ax, br.w - bl.w, bl.w); o.w = fmaf(ay, b - t, t);
-  return o;
-}
-
-// warped rows 2m-1 (bsel 0) and 2m (bsel 1), u = 0..BU-1 <-> x = x0 - 4 + u
-template <typename G, bool HAS_FLOW, bool ALL_IN, typename T>
+// warped rows 2m-1 (bsel 0) and 2m (bsel 1), u = 0..BU-1 <-> x = x0 - 4 + u.
+// wsc[e] = the 4 bilinear weights of slab pixel e (already times 1/C for fp32; zero outside the image),
+// psc[e] = {linear index of the top-left corner, float4 offset of the pixel inside the slab slot}.
+// Software pipeline: the corner loads of item i + GD are issued before item i is blended, so every lane keeps
+// 4 * GD .. 4 * (GD + 1) LDG.128 in flight for the whole slab instead of one latency exposure per batch (the loop is
+// fully unrolled; the ring of corner registers is indexed at compile time).
+template <typename G, bool HAS_FLOW, typename T>
 __device__ __forceinline__ void gather_slab(const T* __restrict__ c2, const Params& P, float4* __restrict__ sB_slot,
-                                            const int4* __restrict__ scratch, int lane) {
-  // LPP lanes per pixel, KQ channel chunks per lane; NIT items are loaded before any is used.
-  // ALL_IN: every pixel of the slab lies inside the image (warp-uniform), so there is no per-item predicate.
+                                            const float4* __restrict__ wsc, const int2* __restrict__ psc, int lane,
+                                            float inv_c) {
+  // LPP lanes per pixel, KQ channel chunks per lane
   constexpr int PPI = 32 / G::LPP;               // pixels per warp iteration
   constexpr int NITEMS = G::NPIX * G::KQ / PPI;  // per-lane items of the slab
-  constexpr int NIT = NITEMS % 4 == 0 ? 4 : 2;
-  static_assert(NITEMS % NIT == 0, "gather batching");
+  constexpr int GD = HAS_FLOW ? 3 : 6;           // items in flight ahead of the one being blended
+  static_assert((G::NPIX * G::KQ) % PPI == 0 && NITEMS > GD, "gather items");
   constexpr int CELT = G::KV * 4;                // channels (compile-time: corner offsets become immediates)
+  constexpr bool HALF = ElemTraits<T>::kIsHalf;
   const int sub = lane / G::LPP, kvl = lane % G::LPP;
-  const size_t rowstride = (size_t)P.W * CELT;
-#pragma unroll 1
-  for (int i0 = 0; i0 < NITEMS; i0 += NIT) {
-    float4 tl[NIT], tr[NIT], bl[NIT], br[NIT];
-    int4 cd[NIT];
+  const T* c2k = c2 + 4 * kvl;
+  const T* c2k1 = c2k + (size_t)P.W * CELT;
+  float4 tl[GD + 1], tr[GD + 1], bl[GD + 1], br[GD + 1];
+  int off[GD + 1];
 #pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-      const int item = i0 + it;  // item -> (pixel group, kv chunk): the chunks of a pixel are adjacent items
-      const int e = (item / G::KQ) * PPI + sub, q = item % G::KQ;
-      cd[it] = scratch[e];
-      const int kv = kvl + q * G::LPP;
-      cd[it].w += kv * G::B_PLANE;
-      const bool ok = ALL_IN || cd[it].x >= 0;
-      const T* base = c2 + (size_t)(ok ? cd[it].x : 0) * CELT + 4 * kv;
-      tl[it] = ld4(base);
+  for (int i = 0; i < NITEMS + GD; ++i) {
+    if (i < NITEMS) {  // item -> (pixel group, kv chunk): the chunks of a pixel are adjacent items
+      const int r = i % (GD + 1);
+      const int e = (i / G::KQ) * PPI + sub, q = i % G::KQ;
+      const int2 ps = psc[e];
+      off[r] = ps.y + kvl + q * G::LPP;
+      const size_t o = (size_t)ps.x * CELT + 4 * q * G::LPP;
+      tl[r] = ld4(c2k + o);
       if (HAS_FLOW) {
-        tr[it] = ld4(base + CELT);
-        bl[it] = ld4(base + rowstride);
-        br[it] = ld4(base + rowstride + CELT);
+        tr[r] = ld4(c2k + o + CELT);
+        bl[r] = ld4(c2k1 + o);
+        br[r] = ld4(c2k1 + o + CELT);
       }
     }
-#pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-      float4 v = tl[it];
-      if (HAS_FLOW)
-        v = round4<T>(bilerp4_fast(tl[it], tr[it], bl[it], br[it], __int_as_float(cd[it].y), __int_as_float(cd[it].z)));
-      if (!ALL_IN && cd[it].x < 0) v = make_float4(0.f, 0.f, 0.f, 0.f);
-      sB_slot[cd[it].w] = v;
+    if (i >= GD) {
+      const int c = i - GD, r = c % (GD + 1);
+      const int e = (c / G::KQ) * PPI + sub;
+      const float4 w = wsc[e];
+      u64 lo = fmul2s(w.x, pack2(tl[r].x, tl[r].y)), hi = fmul2s(w.x, pack2(tl[r].z, tl[r].w));
+      if (HAS_FLOW) {
+        ffma2s(lo, w.y, pack2(tr[r].x, tr[r].y)); ffma2s(hi, w.y, pack2(tr[r].z, tr[r].w));
+        ffma2s(lo, w.z, pack2(bl[r].x, bl[r].y)); ffma2s(hi, w.z, pack2(bl[r].z, bl[r].w));
+        ffma2s(lo, w.w, pack2(br[r].x, br[r].y)); ffma2s(hi, w.w, pack2(br[r].z, br[r].w));
+      }
+      const float2 a = unpack2(lo), b = unpack2(hi);
+      float4 v = make_float4(a.x, a.y, b.x, b.y);
+      if (HALF) {  // the reference's warp output is a 16-bit tensor: round, then apply the channel-mean factor
+        v = round4<T>(v);
+        v.x *= inv_c; v.y *= inv_c; v.z *= inv_c; v.w *= inv_c;
+      }
+      sB_slot[off[r]] = v;
     }
   }
 }
 
-template <typename G, bool HAS_FLOW, typename T, typename TF>
-__device__ __forceinline__ void produce_slab(const T* __restrict__ c2, const TF* __restrict__ flow, const Params& P,
-                                             const Seg& sg, int m, float4* __restrict__ sB_slot,
-                                             int4* __restrict__ scratch, int lane) {
-  __syncwarp();  // every lane is done reading the previous slab's scratch
-  // phase 1: per pixel {top-left corner index or -1, ax, ay, smem offset} -> per-warp scratch.
-  // All flow loads are issued before any is used (one latency exposure for the whole slab).
-  constexpr int NP1 = (G::NPIX + 31) / 32;
+// flow of the slab's pixels (lane handles pixels e = i * 32 + lane); loads only, consumed by slab_coords
+template <typename G, bool HAS_FLOW, typename TF>
+struct SlabFlow {
+  static constexpr int NP1 = (G::NPIX + 31) / 32;
   TF f0[NP1], f1[NP1];
-  bool inside[NP1];
-  bool all_in = true;
+  __device__ __forceinline__ void load(const TF* __restrict__ flow, const Params& P, const Seg& sg, int m, int lane) {
 #pragma unroll
-  for (int i = 0; i < NP1; ++i) {
-    const int e = i * 32 + lane;
-    const int bsel = e / G::BU, u = e - bsel * G::BU;
-    const int y = 2 * m - 1 + bsel, x = sg.x0 - R + u;
-    inside[i] = e < G::NPIX && y >= 0 && y < P.H && x >= 0 && x < P.W;
-    if (e < G::NPIX && !inside[i]) all_in = false;
-    f0[i] = f1[i] = TF(0.0f);
-    if (HAS_FLOW && inside[i]) {
-      const size_t p = ((size_t)sg.b * P.H + y) * P.W + x;
-      f0[i] = flow[2 * p];
-      f1[i] = flow[2 * p + 1];
+    for (int i = 0; i < NP1; ++i) {
+      const int e = i * 32 + lane;
+      const int bsel = e / G::BU, u = e - bsel * G::BU;
+      const int y = 2 * m - 1 + bsel, x = sg.x0 - R + u;
+      const bool inside = e < G::NPIX && y >= 0 && y < P.H && x >= 0 && x < P.W;
+      f0[i] = f1[i] = TF(0.0f);
+      if (HAS_FLOW && inside) {
+        const size_t p = ((size_t)sg.b * P.H + y) * P.W + x;
+        f0[i] = flow[2 * p];
+        f1[i] = flow[2 * p + 1];
+      }
     }
   }
+};
+
+// per pixel weights / corner index -> per-warp scratch
+template <typename G, bool HAS_FLOW, typename T, typename TF>
+__device__ __forceinline__ void slab_coords(const SlabFlow<G, HAS_FLOW, TF>& F, const Params& P, const Seg& sg, int m,
+                                            float4* __restrict__ wsc, int2* __restrict__ psc, int lane, float inv_c) {
+  const float wscale = ElemTraits<T>::kIsHalf ? 1.0f : inv_c;
 #pragma unroll
-  for (int i = 0; i < NP1; ++i) {
+  for (int i = 0; i < SlabFlow<G, HAS_FLOW, TF>::NP1; ++i) {
     const int e = i * 32 + lane;
     if (e < G::NPIX) {
       const int bsel = e / G::BU, u = e - bsel * G::BU;
       const int y = 2 * m - 1 + bsel, x = sg.x0 - R + u;
-      int4 cd = make_int4(-1, 0, 0, (u + u / PX) * 2 + bsel);
-      if (inside[i]) {
+      const bool inside = y >= 0 && y < P.H && x >= 0 && x < P.W;
+      // outside the image the cost volume sees zeros (padding after warping): zero weights on a valid address
+      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+      int pix = sg.b * P.H * P.W;
+      if (inside) {
         if (HAS_FLOW) {
-          const SampleCoord s = sample_coord_v<T, TF>(f0[i], f1[i], P.flow_scale, sg.b, y, x, P.H, P.W);
-          cd.x = s.pix; cd.y = __float_as_int(s.ax); cd.z = __float_as_int(s.ay);
+          const SampleCoord s = sample_coord_v<T, TF>(F.f0[i], F.f1[i], P.flow_scale, sg.b, y, x, P.H, P.W);
+          pix = s.pix;
+          const float w11 = s.ax * s.ay;
+          const float w01 = s.ax - w11, w10 = s.ay - w11;
+          const float w00 = (1.0f - s.ax) - w10;
+          w = make_float4(w00 * wscale, w01 * wscale, w10 * wscale, w11 * wscale);
         } else {
-          cd.x = (sg.b * P.H + y) * P.W + x;
+          pix += y * P.W + x;
+          w.x = wscale;
         }
       }
-      scratch[e] = cd;
+      wsc[e] = w;
+      psc[e] = make_int2(pix, bsel * G::BROW + u * G::KV + (u / PX) * G::BXPAD);
     }
   }
-  all_in = __all_sync(0xffffffffu, all_in);  // also orders the scratch writes before the reads below
-  if (all_in) gather_slab<G, HAS_FLOW, true, T>(c2, P, sB_slot, scratch, lane);
-  else        gather_slab<G, HAS_FLOW, false, T>(c2, P, sB_slot, scratch, lane);
 }
 
 // ---- per-lane correlation: 1 row x 8 pixels x 9 dx against ONE warped row, kv in [kv0, kv1) ------------
+// acc[p][d] = (sum over even channel pairs, sum over odd channel pairs) of c1[p] * warped[p + d]
 template <typename G>
-__device__ __forceinline__ void correlate(const float4* __restrict__ ap, const float4* __restrict__ bp, int kv0,
-                                          int kv1, float (&acc)[PX][ND]) {
+__device__ __forceinline__ void correlate(const ulonglong2* __restrict__ ap, const ulonglong2* __restrict__ bp,
+                                          int kv0, int kv1, u64 (&acc)[PX][ND]) {
+  // Unrolled by KU channel quads: with a rolled loop ptxas rotates the 72 accumulator pairs through ~100 MOVs per
+  // iteration.  kv1 - kv0 is KV or KV / KP, both multiples of KU.
+  constexpr int KU = G::KU;
 #pragma unroll 1
-  for (int kv = kv0; kv < kv1; ++kv) {
-    // pixel-major order: the warped window slides (9 live float4), the c1 operand lives for one pixel only
-    float4 bw[PX + 2 * R];
+  for (int kvb = kv0; kvb < kv1; kvb += KU) {
 #pragma unroll
-    for (int k = 0; k < ND; ++k) bw[k] = bp[kv * G::B_PLANE + (k + k / PX) * 2];
+    for (int ku = 0; ku < KU; ++ku) {
+      const int kv = kvb + ku;
+      ulonglong2 a[PX];
 #pragma unroll
-    for (int p = 0; p < PX; ++p) {
-      if (p > 0) bw[p + ND - 1] = bp[kv * G::B_PLANE + ((p + ND - 1) + (p + ND - 1) / PX) * 2];
-      const float4 a = ap[kv * G::A_PLANE + p];
+      for (int p = 0; p < PX; ++p) a[p] = ap[kv + p * G::KV];
 #pragma unroll
-      for (int d = 0; d < ND; ++d) fma4(acc[p][d], a, bw[p + d]);
+      for (int j = 0; j < PX + 2 * R; ++j) {
+        const ulonglong2 b = bp[kv + j * G::KV + (j / PX) * G::BXPAD];
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+          const int d = j - p;
+          if (d >= 0 && d < ND) {
+            ffma2(acc[p][d], a[p].x, b.x);
+            ffma2(acc[p][d], a[p].y, b.y);
+          }
+        }
+      }
     }
   }
 }
 
-template <int KV, int NXG, bool HAS_FLOW, typename T, typename TF>
+template <int KV, int NXG, bool HAS_FLOW, bool ATMA, typename T, typename TF>
 __global__ void __launch_bounds__(NTHREADS, 1)
 fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* __restrict__ flow,
                   T* __restrict__ out, const Params P) {
   using G = Geo<KV, NXG>;
-  extern __shared__ __align__(16) unsigned char smem[];
+  static_assert(!ATMA || std::is_same<T, float>::value, "TMA delivers c1 as stored: fp32 only");
+  extern __shared__ __align__(128) unsigned char smem[];
   float4* sB = reinterpret_cast<float4*>(smem + G::OFF_B);
   float4* sA = reinterpret_cast<float4*>(smem + G::OFF_A);
   float* sStage = reinterpret_cast<float*>(smem + G::OFF_STAGE);
@@ -304,13 +426,16 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
   uint64_t* fullA = emptyB + NBB;
   uint64_t* emptyA = fullA + NBA;
   Seg* segs = reinterpret_cast<Seg*>(smem + G::OFF_SEG);
-  int* s_misc = reinterpret_cast<int*>(smem + G::OFF_SEG + MAXSEG * 32);  // [0] nseg, [1] total tasks, [2] task counter
+  int* s_misc = reinterpret_cast<int*>(smem + G::OFF_SEG + MAXSEG * 32);  // [0] nseg, [1] total tasks, [2] task counter, [3] pairs
+  int* a_cnt = reinterpret_cast<int*>(smem + G::OFF_ACNT);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int tr_n = 0;
 
   if (tid == 0) {
     for (int i = 0; i < NBB; ++i) { mbar_init(&fullB[i], 32); mbar_init(&emptyB[i], G::EMPTYB_COUNT); }
-    for (int i = 0; i < NBA; ++i) { mbar_init(&fullA[i], 32); mbar_init(&emptyA[i], 6); }
+    for (int i = 0; i < NBA; ++i) { mbar_init(&fullA[i], ATMA ? 1 : 32); mbar_init(&emptyA[i], 6); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the async (TMA) proxy
     // this CTA's contiguous range of (strip, pair) units, cut into per-strip segments
     const long long qlo = P.Q * blockIdx.x / gridDim.x, qhi = P.Q * (blockIdx.x + 1) / gridDim.x;
     int n = 0, task = 0, j = 0, a = 0;
@@ -331,60 +456,93 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
       segs[n++] = s;
       q += p1 - p0;
     }
-    s_misc[0] = n; s_misc[1] = task; s_misc[2] = 0;
+    s_misc[0] = n; s_misc[1] = task; s_misc[2] = 0; s_misc[3] = a;
+    for (int i = 0; i < G::NAP; ++i) a_cnt[i] = 0;
   }
   __syncthreads();
   const int nseg = s_misc[0];
 
   if (warp >= NCW) {
     // =========================== producers ===========================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER));
     const int pwarp = warp - NCW;
-    int4* scratch = reinterpret_cast<int4*>(smem + G::OFF_SCRATCH) + pwarp * G::NPIX;
+    float4* wsc = reinterpret_cast<float4*>(smem + G::OFF_SCRW) + pwarp * G::NPIX;
+    int2* psc = reinterpret_cast<int2*>(smem + G::OFF_SCRP) + pwarp * G::NPIX;
     const float inv_c = 1.0f / (float)P.C;
-    for (int si = 0; si < nseg; ++si) {
+    // slabs owned by this warp, in order; the flow of the next owned slab is loaded while the current one is gathered
+    int si = 0, l = -1;
+    auto advance = [&]() {  // -> next (si, l) with (j0 + l) % NPW == pwarp, or si == nseg
+      for (;;) {
+        if (si >= nseg) return;
+        ++l;
+        if (l >= segs[si].nslab) { ++si; l = -1; continue; }
+        if ((segs[si].j0 + l) % NPW == pwarp) return;
+      }
+    };
+    auto slab_live = [&](int m) { return 2 * m >= 0 && 2 * m - 1 < P.H; };  // else entirely outside the image
+    if constexpr (ATMA) {  // initial fill of the c1 ring; afterwards the consumer that frees a slot refills it
+      const int npairs = s_misc[3];
+      if (pwarp == 0 && lane < G::NAP && lane < npairs) refill_pair_tma<G>(c1, P, segs, nseg, lane, sA, fullA);
+    }
+    SlabFlow<G, HAS_FLOW, TF> F;
+    advance();
+    if (si < nseg && slab_live(segs[si].p0 - 2 + l)) F.load(flow, P, segs[si], segs[si].p0 - 2 + l, lane);
+    while (si < nseg) {
       const Seg sg = segs[si];
-      for (int l = 0; l < sg.nslab; ++l) {
-        const int jg = sg.j0 + l;
-        if (jg % NPW != pwarp) continue;
-        const int m = sg.p0 - 2 + l;
-        if (P.pf_dist > 0) prefetch_rows<G, T, TF>(c1, c2, flow, P, sg, 2 * (m + P.pf_dist) + 2, lane);
+      const int jg = sg.j0 + l, m = sg.p0 - 2 + l;
+      PWC_TR(1, jg);
+      if (P.pf_dist > 0) prefetch_rows<G, T, TF>(c1, c2, flow, P, sg, 2 * (m + P.pf_dist) + 2, lane);
+      if constexpr (!ATMA) {
         if (sg.p0 + l < sg.p1) {
           const int ag = sg.a0 + l, slot = ag % G::NAP, prev = ag - G::NAP;
           if (prev >= 0) mbar_wait(&emptyA[prev % NBA], (prev / NBA) & 1);  // previous occupant fully consumed
-          if (!(P.dbg & 2)) produce_pair<G, T>(c1, P, sg, sg.p0 + l, sA + (size_t)slot * G::ASLOT, lane, inv_c);
+          if (!(P.dbg & 2)) produce_pair<G, T>(c1, P, sg, sg.p0 + l, sA + (size_t)slot * G::ASLOT, lane);
           mbar_arrive(&fullA[ag % NBA]);
         }
-        const int slot = jg % G::NSLAB, prev = jg - G::NSLAB;
-        if (prev >= 0) mbar_wait(&emptyB[prev % NBB], (prev / NBB) & 1);
-        if (2 * m >= 0 && 2 * m - 1 < P.H && !(P.dbg & 2))  // slabs entirely outside the image are never read
-          produce_slab<G, HAS_FLOW, T, TF>(c2, flow, P, sg, m, sB + (size_t)slot * G::BSLOT, scratch, lane);
-        mbar_arrive(&fullB[jg % NBB]);
       }
+      PWC_TR(2, jg);
+      const int slot = jg % G::NSLAB, prev = jg - G::NSLAB;
+      const bool live = slab_live(m) && !(P.dbg & 2);
+      __syncwarp();  // every lane is done reading the previous slab's scratch
+      if (live) slab_coords<G, HAS_FLOW, T, TF>(F, P, sg, m, wsc, psc, lane, inv_c);
+      __syncwarp();
+      advance();
+      if (si < nseg && slab_live(segs[si].p0 - 2 + l)) F.load(flow, P, segs[si], segs[si].p0 - 2 + l, lane);
+      PWC_TR(3, jg);
+      if (prev >= 0) mbar_wait(&emptyB[prev % NBB], (prev / NBB) & 1);
+      PWC_TR(4, jg);
+      if (live) gather_slab<G, HAS_FLOW, T>(c2, P, sB + (size_t)slot * G::BSLOT, wsc, psc, lane, inv_c);
+      mbar_arrive(&fullB[jg % NBB]);
+      PWC_TR(5, jg);
     }
     return;
   }
 
   // =========================== compute warps ===========================
-  // lane = lo + 2*xg + 2*NXG*hi.  Full task f of group g: combo c = f*NH + hi -> slab 4g + c/8, c1 row 2m-4 + c%8,
-  // lo = warped row of the slab.  Edge task: hi = (slab ms, channel part); lo = half:
+  // Full task f of group g: lane = lo + 2*hi + 2*NH*xg ; combo c = f*NH + hi -> slab 4g + c/8, c1 row 2m-4 + c%8,
+  // lo = warped row of the slab.  Edge task: lane = lo + 2*xg + 2*NXG*hi, hi = (slab ms, channel part); lo = half:
   //   half 0: c1 row 2m+4 vs warped row 2m (dy=-4) ; half 1: c1 row 2m-5 vs warped row 2m-1 (dy=+4).
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_COMPUTE));
   float* stage = sStage + warp * G::STAGE_WORDS;
   const int total_tasks = s_misc[1];
-  const int lo = lane & 1, xg = (lane >> 1) % NXG, hi = lane / (2 * NXG);
+  const int lo = lane & 1;
   while (true) {
     int t = 0;
     if (lane == 0) t = atomicAdd(&s_misc[2], 1);
     t = __shfl_sync(0xffffffffu, t, 0);
     if (t >= total_tasks) break;
+    PWC_TR(8, t);
     int si = 0;
     while (si + 1 < nseg && segs[si + 1].task0 <= t) ++si;
     const Seg sg = segs[si];
     const int tl = t - sg.task0, g = tl / G::TPG, rr = tl - G::TPG * g;
     const bool is_edge = rr == G::NF;
 
-    int l, k, sub, bsel, kv0 = 0, kv1 = KV;
+    int l, k, sub, bsel, xg, kv0 = 0, kv1 = KV;
     bool arrive_b, arrive_a;
     if (!is_edge) {
+      const int hi = (lane >> 1) % G::NH;
+      xg = lane / (2 * G::NH);
       const int c = rr * G::NH + hi;
       l = GS * g + (c >> 3);
       const int r8 = c & 7;
@@ -394,6 +552,8 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
       arrive_b = lo == 0 && xg == 0 && (hi == 0 || r8 == 0);
       arrive_a = lo == 0 && xg == 0 && sub == 0;
     } else {
+      const int hi = lane / (2 * NXG);
+      xg = (lane >> 1) % NXG;
       const int ms = hi / G::KP, part = hi % G::KP;
       l = GS * g + ms;
       k = sg.p0 - 2 + l + (lo == 0 ? 2 : -3);
@@ -412,34 +572,35 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
     const int ag = sg.a0 + (pair_ok ? k - sg.p0 : 0), sa = ag % G::NAP;
     if (slab_ok) mbar_wait(&fullB[jg % NBB], (jg / NBB) & 1);
     if (pair_ok) mbar_wait(&fullA[ag % NBA], (ag / NBA) & 1);
+    PWC_TR(9, t);
     const int yb = 2 * m - 1 + bsel, ya = 2 * k + sub;
     const bool store = pair_ok && ya < P.H;
     const bool active = store && yb >= 0 && yb < P.H;
 
-    float acc[PX][ND];
+    u64 acc[PX][ND];
 #pragma unroll
     for (int p = 0; p < PX; ++p)
 #pragma unroll
-      for (int d = 0; d < ND; ++d) acc[p][d] = 0.f;
+      for (int d = 0; d < ND; ++d) acc[p][d] = 0ull;
     if (active && !(P.dbg & 1)) {
-      const float4* ap = sA + (size_t)sa * G::ASLOT + sub * G::A_ROWSLOTS + xg * (PX + 1);
-      const float4* bp = sB + (size_t)sb * G::BSLOT + xg * (PX + 1) * 2 + bsel;
+      const ulonglong2* ap = reinterpret_cast<const ulonglong2*>(sA + (size_t)sa * G::ASLOT + sub * G::AROW + xg * G::AXG);
+      const ulonglong2* bp = reinterpret_cast<const ulonglong2*>(sB + (size_t)sb * G::BSLOT + bsel * G::BROW + xg * G::BXG);
       correlate<G>(ap, bp, kv0, kv1, acc);
     }
     __syncwarp();
+    PWC_TR(10, t);
     // release the ring slots: one arrival per (task, slab) and per (task, slab, pair)
     if (slab_ok && arrive_b) mbar_arrive(&emptyB[jg % NBB]);
-    if (pair_ok && arrive_a) mbar_arrive(&emptyA[ag % NBA]);
-    if (G::KP > 1 && is_edge) {  // channel parts sit in adjacent hi values: butterfly over those lane bits
-#pragma unroll
-      for (int p = 0; p < PX; ++p)
-#pragma unroll
-        for (int d = 0; d < ND; ++d) {
-          float v = acc[p][d];
-          if (G::KP >= 2) v += __shfl_xor_sync(0xffffffffu, v, 2 * NXG);
-          if (G::KP >= 4) v += __shfl_xor_sync(0xffffffffu, v, 4 * NXG);
-          acc[p][d] = v;
+    if (pair_ok && arrive_a) {
+      if constexpr (ATMA) {
+        __threadfence_block();
+        if (atomicAdd(&a_cnt[sa], 1) == 5) {  // last of the 6 arrivals: the slot is free, refill it with pair ag + NAP
+          a_cnt[sa] = 0;
+          if (ag + G::NAP < s_misc[3]) refill_pair_tma<G>(c1, P, segs, nseg, ag + G::NAP, sA, fullA);
         }
+      } else {
+        mbar_arrive(&emptyA[ag % NBA]);
+      }
     }
 
     // epilogue: lane L owns, for each pixel p, the 9 channels [dyi*9, dyi*9+9) of pixel (ya, xb+p).
@@ -459,17 +620,32 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
       nv[it] = __shfl_sync(0xffffffffu, my_nv, l2);
       optr[it] = out + o + w;
     }
-#pragma unroll
-    for (int p = 0; p < PX; ++p) {
+    // software pipeline over the pixels: pixel p + 1 is staged while pixel p is read back and stored
+    auto stage_pixel = [&](int p) {
       float* stg = stage + (p & 1) * (G::STAGE_WORDS / 2);
 #pragma unroll
-      for (int d = 0; d < ND; ++d) stg[lane * 9 + d] = fmaxf(0.1f * acc[p][d], acc[p][d]);
-      __syncwarp();
+      for (int d = 0; d < ND; ++d) {
+        const float2 h = unpack2(acc[p][d]);
+        float v = h.x + h.y;
+        if (G::KP > 1 && is_edge) {  // channel parts sit in adjacent hi values: butterfly over those lane bits
+          if (G::KP >= 2) v += __shfl_xor_sync(0xffffffffu, v, 2 * NXG);
+          if (G::KP >= 4) v += __shfl_xor_sync(0xffffffffu, v, 4 * NXG);
+        }
+        stg[lane * 9 + d] = fmaxf(0.1f * v, v);
+      }
+    };
+    stage_pixel(0);
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+      if (p + 1 < PX) stage_pixel(p + 1);
+      const float* stg = stage + (p & 1) * (G::STAGE_WORDS / 2);
 #pragma unroll
       for (int it = 0; it < 9; ++it)
         if (p < nv[it] && !(P.dbg & 4)) optr[it][p * D] = ElemTraits<T>::from_f(stg[it * 32 + lane]);
+      __syncwarp();
     }
-    __syncwarp();
+    PWC_TR(11, t);
   }
 }
 
@@ -497,7 +673,14 @@ int launch_cfg(const T* c1, const T* c2, const TF* flow, float flow_scale, T* ou
     kern<<<(unsigned)grid, NTHREADS, G::SMEM_BYTES, st>>>(c1, c2, flow, out, P);
     return 0;
   };
-  return flow != nullptr ? go(fwd_stream_kernel<KV, NXG, true, T, TF>) : go(fwd_stream_kernel<KV, NXG, false, T, TF>);
+  // TMA needs 16-byte aligned global rows: C % 4 == 0 and an aligned base (checked by the caller)
+  if constexpr (std::is_same<T, float>::value) {
+    if (!(dbg & 8))
+      return flow != nullptr ? go(fwd_stream_kernel<KV, NXG, true, true, T, TF>)
+                             : go(fwd_stream_kernel<KV, NXG, false, true, T, TF>);
+  }
+  return flow != nullptr ? go(fwd_stream_kernel<KV, NXG, true, false, T, TF>)
+                         : go(fwd_stream_kernel<KV, NXG, false, false, T, TF>);
 }
 
 // Covered: dense output (pixel stride 81), C in {16, 32, 64, 96, 128}.  Everything else returns 1 (caller falls back).

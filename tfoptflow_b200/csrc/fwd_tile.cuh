@@ -40,7 +40,7 @@ struct Cfg {
 
 template <int R, typename T, typename TF>
 #ifndef PWC_TILE_MAXNREG
-#define PWC_TILE_MAXNREG 112
+#define PWC_TILE_MAXNREG 96   /* 2 CTAs/SM (9 warps x 96 regs x 2); measured faster than 112 regs x 1 CTA */
 #endif
 __global__ void __maxnreg__(PWC_TILE_MAXNREG)
 fwd_tile_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* __restrict__ flow,

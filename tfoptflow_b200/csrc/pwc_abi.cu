@@ -375,6 +375,19 @@ int pwc_set_option(const char* key, int value) {
   }
   return fail(PWC_ERR_BAD_ARG, "unknown option '%s'", key);
 }
+int pwc_debug_read_trace(void* dst_host, int max_bytes) {
+#ifdef PWC_HAVE_STREAM_KERNEL
+  if (!dst_host || max_bytes <= 0) return fail(PWC_ERR_BAD_ARG, "null argument");
+  size_t n = sizeof(unsigned long long) * (pwc::stream::NCW + pwc::stream::NPW) * pwc::stream::TRACE_LEN;
+  if ((size_t)max_bytes < n) n = (size_t)max_bytes;
+  if (cudaDeviceSynchronize() != cudaSuccess ||
+      cudaMemcpyFromSymbol(dst_host, pwc::stream::g_trace, n, 0, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return fail(PWC_ERR_CUDA, "trace copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return (int)n;
+#else
+  return fail(PWC_ERR_BAD_ARG, "built without the streaming kernel");
+#endif
+}
 int pwc_get_option(const char* key, int* value) {
   if (!key || !value) return fail(PWC_ERR_BAD_ARG, "null argument");
   if (!strcmp(key, "fwd_impl")) { *value = g_fwd_impl.load(); return PWC_OK; }
