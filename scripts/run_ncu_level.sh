@@ -1,4 +1,6 @@
+# usage: run_ncu_level.sh <out-name> [time_level args...]   (plain run first, then one ncu --set full capture)
 set -e
-python scripts/time_level.py 32 3 > gpurun_out/plain_tl.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:fwd_stream -s 6 -c 1 -f -o gpurun_out/prof_r01_v3a_stream_L2 python scripts/time_level.py 32 3 > gpurun_out/ncu_tl.log 2>&1
-tail -2 gpurun_out/plain_tl.log
+out=$1; shift
+python scripts/time_level.py 32 3 "$@" > gpurun_out/plain_tl.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:fwd_stream -s 6 -c 1 -f -o gpurun_out/$out python scripts/time_level.py 32 3 "$@" > gpurun_out/ncu_tl.log 2>&1
+tail -1 gpurun_out/plain_tl.log

@@ -12,10 +12,7 @@ import pytest
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from stream_protocol_sim import lane_tasks, segments, simulate  # noqa: E402
 
-PX = 8
-
-
-def run_cta(B, H, W, NXG, grid, cta, written, slab_arr, pair_arr):
+def run_cta(B, H, W, NXG, grid, cta, written, slab_arr, pair_arr, PX=8):
     TW = PX * NXG
     segs, total = segments(B, H, W, TW, NXG, grid, cta)
     for t in range(total):
@@ -37,14 +34,14 @@ def run_cta(B, H, W, NXG, grid, cta, written, slab_arr, pair_arr):
     return segs
 
 
-@pytest.mark.parametrize("NXG", [4, 2, 1])
+@pytest.mark.parametrize("NXG,PX", [(4, 8), (4, 6), (2, 8), (1, 8)])
 @pytest.mark.parametrize("B,H,W,grid", [(2, 12, 40, 3), (1, 7, 33, 5), (3, 10, 64, 7), (1, 112, 32, 4), (2, 5, 8, 1),
                                         (1, 2, 2, 1), (4, 6, 70, 11)])
-def test_stream_schedule_covers_every_output_once(B, H, W, grid, NXG):
+def test_stream_schedule_covers_every_output_once(B, H, W, grid, NXG, PX):
     written, slab_arr, pair_arr = collections.Counter(), collections.Counter(), collections.Counter()
     nslab = npair = 0
     for cta in range(grid):
-        segs = run_cta(B, H, W, NXG, grid, cta, written, slab_arr, pair_arr)
+        segs = run_cta(B, H, W, NXG, grid, cta, written, slab_arr, pair_arr, PX)
         nslab += sum(s["nslab"] for s in segs)
         npair += sum(s["p1"] - s["p0"] for s in segs)
     assert len(written) == B * H * W * 9 and set(written.values()) == {1}

@@ -32,42 +32,64 @@ namespace stream {
 
 typedef unsigned long long u64;
 
-constexpr int R = 4, ND = 9, D = 81, PX = 8;
+constexpr int R = 4, ND = 9, D = 81;
 constexpr int NCW = 8;   // compute warps (two warpgroups)
 constexpr int NPW = 4;   // producer warps (one warpgroup)
 constexpr int NTHREADS = 32 * (NCW + NPW);
-constexpr int REGS_COMPUTE = 200, REGS_PRODUCER = 104;  // setmaxnreg moves registers inside the CTA allocation: 2*200 + 104 = 3*168
+  // setmaxnreg moves registers inside the CTA allocation: 2*200 + 104 = 3*168
 constexpr int MAXSEG = 8;
 constexpr int GS = 4;    // slabs per task group (one edge task per group)
 constexpr size_t SMEM_LIMIT = 232448;
+#ifndef PWC_STREAM_LD4
+#define PWC_STREAM_LD4 ld4
+#endif
+#ifndef PWC_STREAM_NSLAB8
+#define PWC_STREAM_NSLAB8 8
+#endif
+#ifndef PWC_STREAM_NAP8
+#define PWC_STREAM_NAP8 12
+#endif
+#ifndef PWC_STREAM_GD
+#define PWC_STREAM_GD 3
+#endif
+#ifndef PWC_STREAM_PX32
+#define PWC_STREAM_PX32 6
+#endif
 
 constexpr int pad_to(int v, int r) { return v + ((r - v % 8) + 8) % 8; }  // smallest v' >= v with v' % 8 == r
 
-template <int KV_, int NXG_>
+// PX = pixels per lane-task (8, or 6 where the 72 packed accumulators of 8 pixels leave ptxas no room for a clean
+// rolled channel loop: 54 pairs + operands fit 184 registers and give the producers 136)
+template <int KV_, int NXG_, int PX_ = 8>
 struct Geo {
-  static constexpr int KV = KV_, NXG = NXG_;
+  static constexpr int KV = KV_, NXG = NXG_, PX = PX_;
   static constexpr int TW = PX * NXG;                 // strip width
   static constexpr int BU = TW + 2 * R;               // warped pixels per row (with halo)
   static constexpr int NPIX = 2 * BU;                 // pixels per slab
   // float4 units.  c1 pair slot: [sub(2)][xg][p(8)][kv] ; warped slab slot: [bsel(2)][u(BU)][kv], 2 pads per 8 pixels
-  static constexpr int AXG = 8 * KV + 4;
+  static constexpr int AXG = pad_to(PX * KV, 4);
   static constexpr int AROW = pad_to(NXG * AXG, 1);
   static constexpr int ASLOT = 2 * AROW;
   static constexpr int BXPAD = 2;
-  static constexpr int BXG = 8 * KV + BXPAD;
-  static constexpr int BROW = pad_to(BU * KV + (BU / 8) * BXPAD, 1);
+  static constexpr int BXG = PX * KV + BXPAD;
+  static constexpr int BROW = pad_to(BU * KV + ((BU + PX - 1) / PX) * BXPAD, 1);
   static constexpr int BSLOT = 2 * BROW;
   static_assert(AXG % 8 == 4 && AROW % 8 == 1 && ASLOT % 8 == 2 && BROW % 8 == 1, "bank-group strides");
   static constexpr int NH = 16 / NXG;                 // c1 rows (hi values) per full task
   static constexpr int NF = 8 * GS / NH;              // full tasks per group: 8 / 4 / 2
   static constexpr int TPG = NF + 1;                  // + one edge task
   static constexpr int KP = 4 / NXG;                  // channel split of the edge task
-  static constexpr int KU = (KV / KP) % 8 == 0 ? 8 : ((KV / KP) % 6 == 0 ? 6 : 4);  // unroll of the channel loop
+  // channel-loop unroll: rolled (1) where the accumulators leave room, else long stretches so that the accumulator
+  // shuffling ptxas does at every back-edge of a register-starved loop is amortised
+  static constexpr int KU = PX <= 6 ? 1 : ((KV / KP) % 8 == 0 ? 8 : ((KV / KP) % 6 == 0 ? 6 : 4));
+  // setmaxnreg moves registers inside the CTA allocation (384 x 168): 2 * REGS_COMPUTE + REGS_PRODUCER = 504
+  static constexpr int REGS_COMPUTE = PX <= 6 ? 192 : 200;
+  static constexpr int REGS_PRODUCER = 504 - 2 * REGS_COMPUTE;
   static constexpr int EMPTYB_COUNT = (NXG == 4 ? 2 : 1) + 1;
   static constexpr int LPP = KV >= 8 ? 8 : KV;        // producer lanes per pixel
   static constexpr int KQ = KV / LPP;                 // kv chunks per lane
-  static constexpr int NSLAB = KV == 32 ? 6 : (KV == 16 ? 6 : (KV == 8 ? 8 : 7));
-  static constexpr int NAP = KV == 32 ? 10 : 12;     // even: the wrap-around keeps consecutive pairs 2 bank groups apart
+  static constexpr int NSLAB = KV == 32 ? 6 : (KV == 16 ? (PX <= 6 ? 8 : 6) : (KV == 8 ? PWC_STREAM_NSLAB8 : 7));
+  static constexpr int NAP = KV == 32 ? 10 : (KV == 8 ? PWC_STREAM_NAP8 : 12);     // even: the wrap-around keeps consecutive pairs 2 bank groups apart
   static constexpr int STAGE_WORDS = 640;             // per compute warp (2 x 320, double buffered)
   static constexpr size_t OFF_B = 0;
   static constexpr size_t OFF_A = OFF_B + (size_t)NSLAB * BSLOT * 16;
@@ -145,7 +167,13 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) 
 
 // ---- packed fp32 (sm_100 FFMA2 / FMUL2) ----------------------------------------------------
 __device__ __forceinline__ void ffma2(u64& d, u64 a, u64 b) {
+#ifdef PWC_STREAM_FFMA2_INTRINSIC
+  float2 dd = *reinterpret_cast<float2*>(&d);
+  dd = __ffma2_rn(*reinterpret_cast<const float2*>(&a), *reinterpret_cast<const float2*>(&b), dd);
+  d = *reinterpret_cast<u64*>(&dd);
+#else
   asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+#endif
 }
 // scalar weight x packed pair: ptxas folds the {w, w} pair into the scalar-broadcast operand form
 __device__ __forceinline__ void ffma2s(u64& d, float w, u64 b) {
@@ -171,29 +199,26 @@ __device__ __forceinline__ float2 unpack2(u64 v) {
 }
 
 // ---- producer ------------------------------------------------------------------------------
-// pull the leading edge of a future slab (2 rows of c2, c1 and flow) towards L2
+// pull the leading edge of a future slab (2 rows of c2 and flow) towards L2, one 128-byte line per lane and step
+// (c1 needs no help: its TMA copies are issued a ring length ahead)
 template <typename G, typename T, typename TF>
-__device__ __forceinline__ void prefetch_rows(const T* c1, const T* c2, const TF* flow, const Params& P, const Seg& sg,
-                                              int y0, int lane) {
-  // lanes 0,1: c2 rows y0, y0+1 ; lanes 2,3: c1 ; lanes 4,5: flow.  Ranges are rounded down to 16 bytes.
-  const int r = lane & 1, what = lane >> 1;
-  const int y = y0 + r;
-  if (what > 2 || y < 0 || y >= P.H) return;
-  if (what == 2 && flow == nullptr) return;
+__device__ __forceinline__ void prefetch_rows(const T* c2, const TF* flow, const Params& P, const Seg& sg, int y0,
+                                              int lane) {
   const int xlo = max(sg.x0 - 8, 0), xhi = min(sg.x0 + G::TW + 8, P.W);
-  const size_t rowpix = ((size_t)sg.b * P.H + y) * P.W;
-  uintptr_t lo, hi;
-  if (what == 2) {
-    lo = reinterpret_cast<uintptr_t>(flow + (rowpix + xlo) * 2);
-    hi = reinterpret_cast<uintptr_t>(flow + (rowpix + xhi) * 2);
-  } else {
-    const T* base = what == 0 ? c2 : c1;
-    lo = reinterpret_cast<uintptr_t>(base + (rowpix + xlo) * P.C);
-    hi = reinterpret_cast<uintptr_t>(base + (rowpix + xhi) * P.C);
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int y = y0 + r;
+    if (y < 0 || y >= P.H) continue;
+    const size_t rowpix = ((size_t)sg.b * P.H + y) * P.W;
+    const char* lo = reinterpret_cast<const char*>(c2 + (rowpix + xlo) * P.C);
+    const int nb = (xhi - xlo) * P.C * (int)sizeof(T);
+    for (int o = lane * 128; o < nb; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(lo + o));
+    if (flow != nullptr) {
+      const char* fl = reinterpret_cast<const char*>(flow + (rowpix + xlo) * 2);
+      const int fb = (xhi - xlo) * 2 * (int)sizeof(TF);
+      if (lane * 128 < fb) asm volatile("prefetch.global.L2 [%0];" ::"l"(fl + lane * 128));
+    }
   }
-  lo &= ~uintptr_t(15);
-  hi &= ~uintptr_t(15);
-  if (hi > lo) bulk_prefetch_l2(reinterpret_cast<const void*>(lo), (uint32_t)(hi - lo));
 }
 
 // c1 rows 2k, 2k+1 of the strip by TMA: one bulk copy per (row, 8-pixel group), i.e. 1 KB at C = 32
@@ -207,9 +232,9 @@ __device__ __forceinline__ void produce_pair_tma(const float* __restrict__ c1, c
   __syncwarp();
   if (lane < 2 * G::NXG) {
     const int row = lane / G::NXG, xg = lane % G::NXG;
-    const int y = 2 * k + row, x = sg.x0 + PX * xg;
+    const int y = 2 * k + row, x = sg.x0 + G::PX * xg;
     if (y < P.H && x < P.W) {
-      const int npx = min(PX, P.W - x);
+      const int npx = min(G::PX, P.W - x);
       bulk_g2s(sA_slot + row * G::AROW + xg * G::AXG, c1 + (((size_t)sg.b * P.H + y) * P.W + x) * P.C,
                (uint32_t)(npx * P.C * 4), bar);
     }
@@ -230,8 +255,8 @@ __device__ __forceinline__ void refill_pair_tma(const float* __restrict__ c1, co
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // consumers' generic reads of the slot come first
   mbar_arrive_expect_tx(bar, (uint32_t)(rows * px * P.C * 4));
   for (int row = 0; row < rows; ++row)
-    for (int xg = 0; xg * PX < px; ++xg) {
-      const int x = x0 + PX * xg, npx = min(PX, P.W - x);
+    for (int xg = 0; xg * G::PX < px; ++xg) {
+      const int x = x0 + G::PX * xg, npx = min(G::PX, P.W - x);
       bulk_g2s(slot + row * G::AROW + xg * G::AXG, c1 + (((size_t)b * P.H + 2 * k + row) * P.W + x) * P.C,
                (uint32_t)(npx * P.C * 4), bar);
     }
@@ -258,7 +283,7 @@ __device__ __forceinline__ void produce_pair(const T* __restrict__ c1, const Par
     const int id = it * 32 + lane;
     const int kv = id % G::KV, pxl = id / G::KV;
     const int row = pxl / G::TW, col = pxl - row * G::TW;
-    sA_slot[row * G::AROW + (col / PX) * G::AXG + (col % PX) * G::KV + kv] = v[it];
+    sA_slot[row * G::AROW + (col / G::PX) * G::AXG + (col % G::PX) * G::KV + kv] = v[it];
   }
 }
 
@@ -275,7 +300,7 @@ __device__ __forceinline__ void gather_slab(const T* __restrict__ c2, const Para
   // LPP lanes per pixel, KQ channel chunks per lane
   constexpr int PPI = 32 / G::LPP;               // pixels per warp iteration
   constexpr int NITEMS = G::NPIX * G::KQ / PPI;  // per-lane items of the slab
-  constexpr int GD = HAS_FLOW ? 3 : 6;           // items in flight ahead of the one being blended
+  constexpr int GD = HAS_FLOW ? PWC_STREAM_GD : 6;  // items in flight ahead of the one being blended
   static_assert((G::NPIX * G::KQ) % PPI == 0 && NITEMS > GD, "gather items");
   constexpr int CELT = G::KV * 4;                // channels (compile-time: corner offsets become immediates)
   constexpr bool HALF = ElemTraits<T>::kIsHalf;
@@ -292,11 +317,11 @@ __device__ __forceinline__ void gather_slab(const T* __restrict__ c2, const Para
       const int2 ps = psc[e];
       off[r] = ps.y + kvl + q * G::LPP;
       const size_t o = (size_t)ps.x * CELT + 4 * q * G::LPP;
-      tl[r] = ld4(c2k + o);
+      tl[r] = PWC_STREAM_LD4(c2k + o);
       if (HAS_FLOW) {
-        tr[r] = ld4(c2k + o + CELT);
-        bl[r] = ld4(c2k1 + o);
-        br[r] = ld4(c2k1 + o + CELT);
+        tr[r] = PWC_STREAM_LD4(c2k + o + CELT);
+        bl[r] = PWC_STREAM_LD4(c2k1 + o);
+        br[r] = PWC_STREAM_LD4(c2k1 + o + CELT);
       }
     }
     if (i >= GD) {
@@ -371,7 +396,7 @@ __device__ __forceinline__ void slab_coords(const SlabFlow<G, HAS_FLOW, TF>& F, 
         }
       }
       wsc[e] = w;
-      psc[e] = make_int2(pix, bsel * G::BROW + u * G::KV + (u / PX) * G::BXPAD);
+      psc[e] = make_int2(pix, bsel * G::BROW + u * G::KV + (u / G::PX) * G::BXPAD);
     }
   }
 }
@@ -380,39 +405,43 @@ __device__ __forceinline__ void slab_coords(const SlabFlow<G, HAS_FLOW, TF>& F, 
 // acc[p][d] = (sum over even channel pairs, sum over odd channel pairs) of c1[p] * warped[p + d]
 template <typename G>
 __device__ __forceinline__ void correlate(const ulonglong2* __restrict__ ap, const ulonglong2* __restrict__ bp,
-                                          int kv0, int kv1, u64 (&acc)[PX][ND]) {
+                                          int kv0, int kv1, u64 (&acc)[G::PX][ND]) {
   // Unrolled by KU channel quads: with a rolled loop ptxas rotates the 72 accumulator pairs through ~100 MOVs per
   // iteration.  kv1 - kv0 is KV or KV / KP, both multiples of KU.
   constexpr int KU = G::KU;
+  if (G::KP == 1) { kv0 = 0; kv1 = G::KV; }  // compile-time trip count
 #pragma unroll 1
   for (int kvb = kv0; kvb < kv1; kvb += KU) {
 #pragma unroll
     for (int ku = 0; ku < KU; ++ku) {
       const int kv = kvb + ku;
-      ulonglong2 a[PX];
+      ulonglong2 a[G::PX];
 #pragma unroll
-      for (int p = 0; p < PX; ++p) a[p] = ap[kv + p * G::KV];
+      for (int p = 0; p < G::PX; ++p) a[p] = ap[kv + p * G::KV];
 #pragma unroll
-      for (int j = 0; j < PX + 2 * R; ++j) {
-        const ulonglong2 b = bp[kv + j * G::KV + (j / PX) * G::BXPAD];
+      for (int j = 0; j < G::PX + 2 * R; ++j) {
+        const ulonglong2 b = bp[kv + j * G::KV + (j / G::PX) * G::BXPAD];
+        // all first halves, then all second halves: the two FFMA2 of one accumulator are >= 8 issue slots apart
 #pragma unroll
-        for (int p = 0; p < PX; ++p) {
+        for (int p = 0; p < G::PX; ++p) {
           const int d = j - p;
-          if (d >= 0 && d < ND) {
-            ffma2(acc[p][d], a[p].x, b.x);
-            ffma2(acc[p][d], a[p].y, b.y);
-          }
+          if (d >= 0 && d < ND) ffma2(acc[p][d], a[p].x, b.x);
+        }
+#pragma unroll
+        for (int p = 0; p < G::PX; ++p) {
+          const int d = j - p;
+          if (d >= 0 && d < ND) ffma2(acc[p][d], a[p].y, b.y);
         }
       }
     }
   }
 }
 
-template <int KV, int NXG, bool HAS_FLOW, bool ATMA, typename T, typename TF>
+template <int KV, int NXG, int PXL, bool HAS_FLOW, bool ATMA, typename T, typename TF>
 __global__ void __launch_bounds__(NTHREADS, 1)
 fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* __restrict__ flow,
                   T* __restrict__ out, const Params P) {
-  using G = Geo<KV, NXG>;
+  using G = Geo<KV, NXG, PXL>;
   static_assert(!ATMA || std::is_same<T, float>::value, "TMA delivers c1 as stored: fp32 only");
   extern __shared__ __align__(128) unsigned char smem[];
   float4* sB = reinterpret_cast<float4*>(smem + G::OFF_B);
@@ -464,7 +493,7 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
 
   if (warp >= NCW) {
     // =========================== producers ===========================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G::REGS_PRODUCER));
     const int pwarp = warp - NCW;
     float4* wsc = reinterpret_cast<float4*>(smem + G::OFF_SCRW) + pwarp * G::NPIX;
     int2* psc = reinterpret_cast<int2*>(smem + G::OFF_SCRP) + pwarp * G::NPIX;
@@ -491,7 +520,7 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
       const Seg sg = segs[si];
       const int jg = sg.j0 + l, m = sg.p0 - 2 + l;
       PWC_TR(1, jg);
-      if (P.pf_dist > 0) prefetch_rows<G, T, TF>(c1, c2, flow, P, sg, 2 * (m + P.pf_dist) + 2, lane);
+      if (P.pf_dist > 0) prefetch_rows<G, T, TF>(c2, flow, P, sg, 2 * (m + P.pf_dist) + 2, lane);
       if constexpr (!ATMA) {
         if (sg.p0 + l < sg.p1) {
           const int ag = sg.a0 + l, slot = ag % G::NAP, prev = ag - G::NAP;
@@ -522,7 +551,7 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
   // Full task f of group g: lane = lo + 2*hi + 2*NH*xg ; combo c = f*NH + hi -> slab 4g + c/8, c1 row 2m-4 + c%8,
   // lo = warped row of the slab.  Edge task: lane = lo + 2*xg + 2*NXG*hi, hi = (slab ms, channel part); lo = half:
   //   half 0: c1 row 2m+4 vs warped row 2m (dy=-4) ; half 1: c1 row 2m-5 vs warped row 2m-1 (dy=+4).
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_COMPUTE));
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(G::REGS_COMPUTE));
   float* stage = sStage + warp * G::STAGE_WORDS;
   const int total_tasks = s_misc[1];
   const int lo = lane & 1;
@@ -577,9 +606,9 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
     const bool store = pair_ok && ya < P.H;
     const bool active = store && yb >= 0 && yb < P.H;
 
-    u64 acc[PX][ND];
+    u64 acc[G::PX][ND];
 #pragma unroll
-    for (int p = 0; p < PX; ++p)
+    for (int p = 0; p < G::PX; ++p)
 #pragma unroll
       for (int d = 0; d < ND; ++d) acc[p][d] = 0ull;
     if (active && !(P.dbg & 1)) {
@@ -605,7 +634,7 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
 
     // epilogue: lane L owns, for each pixel p, the 9 channels [dyi*9, dyi*9+9) of pixel (ya, xb+p).
     // Runs go through a per-warp transposition buffer so that each store instruction writes whole runs.
-    const int xb = sg.x0 + xg * PX;
+    const int xb = sg.x0 + xg * G::PX;
     const int dyi = yb - ya + R;
     const bool writer = store && kv0 == 0;
     const long long my_off = writer ? (long long)((((size_t)sg.b * P.H + ya) * P.W + xb) * D + dyi * ND) : 0;
@@ -637,8 +666,8 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
     stage_pixel(0);
     __syncwarp();
 #pragma unroll
-    for (int p = 0; p < PX; ++p) {
-      if (p + 1 < PX) stage_pixel(p + 1);
+    for (int p = 0; p < G::PX; ++p) {
+      if (p + 1 < G::PX) stage_pixel(p + 1);
       const float* stg = stage + (p & 1) * (G::STAGE_WORDS / 2);
 #pragma unroll
       for (int it = 0; it < 9; ++it)
@@ -650,10 +679,10 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
 }
 
 // Host-side launcher.  Returns 0 when launched, 1 when the shape is not covered, -1 on a CUDA error.
-template <int KV, int NXG, typename T, typename TF>
+template <int KV, int NXG, int PXL, typename T, typename TF>
 int launch_cfg(const T* c1, const T* c2, const TF* flow, float flow_scale, T* out, int B, int H, int W, int C,
                cudaStream_t st, int sms, int ctas_override, int pf_dist, int dbg) {
-  using G = Geo<KV, NXG>;
+  using G = Geo<KV, NXG, PXL>;
   Params P;
   P.B = B; P.H = H; P.W = W; P.C = C; P.ops = D; P.flow_scale = flow_scale;
   P.NPAIR = (H + 1) / 2;
@@ -676,11 +705,11 @@ int launch_cfg(const T* c1, const T* c2, const TF* flow, float flow_scale, T* ou
   // TMA needs 16-byte aligned global rows: C % 4 == 0 and an aligned base (checked by the caller)
   if constexpr (std::is_same<T, float>::value) {
     if (!(dbg & 8))
-      return flow != nullptr ? go(fwd_stream_kernel<KV, NXG, true, true, T, TF>)
-                             : go(fwd_stream_kernel<KV, NXG, false, true, T, TF>);
+      return flow != nullptr ? go(fwd_stream_kernel<KV, NXG, PXL, true, true, T, TF>)
+                             : go(fwd_stream_kernel<KV, NXG, PXL, false, true, T, TF>);
   }
-  return flow != nullptr ? go(fwd_stream_kernel<KV, NXG, true, false, T, TF>)
-                         : go(fwd_stream_kernel<KV, NXG, false, false, T, TF>);
+  return flow != nullptr ? go(fwd_stream_kernel<KV, NXG, PXL, true, false, T, TF>)
+                         : go(fwd_stream_kernel<KV, NXG, PXL, false, false, T, TF>);
 }
 
 // Covered: dense output (pixel stride 81), C in {16, 32, 64, 96, 128}.  Everything else returns 1 (caller falls back).
@@ -688,14 +717,14 @@ template <typename T, typename TF>
 int launch(const T* c1, const T* c2, const TF* flow, float flow_scale, T* out, int B, int H, int W, int C,
            int64_t ops, cudaStream_t st, int sms, int ctas_override, int pf_dist, int dbg = 0) {
   if (ops != D) return 1;
-#define PWC_STREAM_GO(KV, NXG) \
-  return launch_cfg<KV, NXG, T, TF>(c1, c2, flow, flow_scale, out, B, H, W, C, st, sms, ctas_override, pf_dist, dbg)
+#define PWC_STREAM_GO(KV, NXG, PXL) \
+  return launch_cfg<KV, NXG, PXL, T, TF>(c1, c2, flow, flow_scale, out, B, H, W, C, st, sms, ctas_override, pf_dist, dbg)
   switch (C) {
-    case 16: PWC_STREAM_GO(4, 4);
-    case 32: PWC_STREAM_GO(8, 4);
-    case 64: PWC_STREAM_GO(16, 2);
-    case 96: PWC_STREAM_GO(24, 1);
-    case 128: PWC_STREAM_GO(32, 1);
+    case 16: PWC_STREAM_GO(4, 4, PWC_STREAM_PX32);
+    case 32: PWC_STREAM_GO(8, 4, PWC_STREAM_PX32);
+    case 64: PWC_STREAM_GO(16, 2, PWC_STREAM_PX32);
+    case 96: PWC_STREAM_GO(24, 1, 8);
+    case 128: PWC_STREAM_GO(32, 1, 8);
     default: return 1;
   }
 #undef PWC_STREAM_GO
