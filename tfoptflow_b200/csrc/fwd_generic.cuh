@@ -35,6 +35,37 @@ fwd_generic_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF*
   }
 }
 
+// Un-warped cost volume (the top pyramid level, model_pwcnet.py:1554) for small images: one thread per output
+// element, 16-byte loads.  A level-6 problem (7 x 16 pixels per image) has too few tiles to fill the GPU with the
+// tiled kernel; here every (pixel, displacement) is its own thread and the operands come out of L1/L2.
+template <typename T>
+__global__ void __launch_bounds__(256)
+fwd_noflow_vec4_kernel(const T* __restrict__ c1, const T* __restrict__ c2, T* __restrict__ out, int B, int H, int W,
+                       int C, int r, int64_t out_pixel_stride) {
+  const int n = 2 * r + 1, D = n * n;
+  const int64_t total = (int64_t)B * H * W * D;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int d = (int)(idx % D);
+    const int64_t p = idx / D;
+    const int x = (int)(p % W), y = (int)((p / W) % H), b = (int)(p / ((int64_t)W * H));
+    const int yy = y + d / n - r, xx = x + d % n - r;
+    float a0 = 0.0f, a1 = 0.0f;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+      const T* a = c1 + (size_t)p * C;
+      const T* w = c2 + (((size_t)b * H + yy) * W + xx) * C;
+      int c = 0;
+      for (; c + 8 <= C; c += 8) {
+        const float4 u0 = ld4(a + c), v0 = ld4(w + c), u1 = ld4(a + c + 4), v1 = ld4(w + c + 4);
+        fma4(a0, u0, v0);
+        fma4(a1, u1, v1);
+      }
+      if (c < C) fma4(a0, ld4(a + c), ld4(w + c));
+    }
+    out[(size_t)p * out_pixel_stride + d] = ElemTraits<T>::from_f(lrelu01((a0 + a1) * (1.0f / (float)C)));
+  }
+}
+
 // dense_image_warp forward, one thread per (pixel, channel)
 template <typename T, typename TF>
 __global__ void __launch_bounds__(256)

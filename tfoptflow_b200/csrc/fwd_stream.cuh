@@ -35,7 +35,7 @@ typedef unsigned long long u64;
 constexpr int R = 4, ND = 9, D = 81;
 constexpr int NCW = 8;   // compute warps (two warpgroups)
 constexpr int NPW = 4;   // producer warps (one warpgroup)
-constexpr int NTHREADS = 32 * (NCW + NPW);
+constexpr int NSW_MAX = 4; // store warps (one warpgroup) of the geometries that stage whole tasks
   // setmaxnreg moves registers inside the CTA allocation: 2*200 + 104 = 3*168
 constexpr int MAXSEG = 8;
 constexpr int GS = 4;    // slabs per task group (one edge task per group)
@@ -51,6 +51,9 @@ constexpr size_t SMEM_LIMIT = 232448;
 #endif
 #ifndef PWC_STREAM_GD
 #define PWC_STREAM_GD 3
+#endif
+#ifndef PWC_STREAM_NSW
+#define PWC_STREAM_NSW 0
 #endif
 #ifndef PWC_STREAM_PX32
 #define PWC_STREAM_PX32 6
@@ -83,23 +86,38 @@ struct Geo {
   // shuffling ptxas does at every back-edge of a register-starved loop is amortised
   static constexpr int KU = PX <= 6 ? 1 : ((KV / KP) % 8 == 0 ? 8 : ((KV / KP) % 6 == 0 ? 6 : 4));
   // setmaxnreg moves registers inside the CTA allocation (384 x 168): 2 * REGS_COMPUTE + REGS_PRODUCER = 504
-  static constexpr int REGS_COMPUTE = PX <= 6 ? 192 : 200;
-  static constexpr int REGS_PRODUCER = 504 - 2 * REGS_COMPUTE;
+  // Store warps: with whole-task staging (PX <= 6) the compute warps only stage their results; NSW extra warps read
+  // the staged runs back and issue the global stores, so the store latency chain never holds an FFMA2 warp.
+  // (measured on level 2: 289 us with store warps against 241 us without - the scheduler slots they take cost more
+  // than the decoupling gains - so they are off by default; -DPWC_STREAM_NSW=4 turns them on)
+  static constexpr int NCWG = PX <= 4 ? 12 : 8;       // compute warps: 3 per scheduler where 36 accumulator pairs leave room
+  static constexpr int NSW = PX <= 6 ? PWC_STREAM_NSW : 0;
+  static constexpr int NTHREADS = 32 * (NCWG + NPW + NSW);
+  // per-thread budget at launch: 65536 / NTHREADS rounded down to 8 -> 168 (384 threads) or 128 (512 threads)
+  static constexpr int REGS_COMPUTE = PX <= 4 ? 136 : (PX <= 6 ? (NSW ? 184 : 192) : 200);
+  static constexpr int REGS_STORE = 56;
+  static constexpr int REGS_PRODUCER = NCWG == 12 ? 512 - 3 * REGS_COMPUTE : (NSW ? 512 - 2 * REGS_COMPUTE - REGS_STORE : 504 - 2 * REGS_COMPUTE);
+  static_assert(NCWG == 8 || NSW == 0, "thread budget");
   static constexpr int EMPTYB_COUNT = (NXG == 4 ? 2 : 1) + 1;
   static constexpr int LPP = KV >= 8 ? 8 : KV;        // producer lanes per pixel
   static constexpr int KQ = KV / LPP;                 // kv chunks per lane
-  static constexpr int NSLAB = KV == 32 ? 6 : (KV == 16 ? (PX <= 6 ? 8 : 6) : (KV == 8 ? PWC_STREAM_NSLAB8 : 7));
-  static constexpr int NAP = KV == 32 ? 10 : (KV == 8 ? PWC_STREAM_NAP8 : 12);     // even: the wrap-around keeps consecutive pairs 2 bank groups apart
-  static constexpr int STAGE_WORDS = 640;             // per compute warp (2 x 320, double buffered)
+  static constexpr int NSLAB = PX <= 4 ? 10 : KV == 32 ? 6 : (KV == 16 ? (PX <= 6 ? 8 : 6) : (KV == 8 ? PWC_STREAM_NSLAB8 : 7));
+  static constexpr int NAP = PX <= 4 ? 14 : KV == 32 ? 10 : (KV == 8 ? PWC_STREAM_NAP8 : 12);     // even: the wrap-around keeps consecutive pairs 2 bank groups apart
+  // transposition buffer per compute warp: all PX pixels at once where shared memory allows (one warp sync per task),
+  // else two pixels, double buffered
+  static constexpr bool FULLSTAGE = PX <= 6;
+  static constexpr int STAGE_WORDS = FULLSTAGE ? 320 * PX : 640;
   static constexpr size_t OFF_B = 0;
   static constexpr size_t OFF_A = OFF_B + (size_t)NSLAB * BSLOT * 16;
   static constexpr size_t OFF_STAGE = OFF_A + (size_t)NAP * ASLOT * 16;
-  static constexpr size_t OFF_SCRW = OFF_STAGE + (size_t)NCW * STAGE_WORDS * 4;   // float4 weights per pixel
+  static constexpr size_t OFF_SCRW = OFF_STAGE + (size_t)NCWG * STAGE_WORDS * 4;   // float4 weights per pixel
   static constexpr size_t OFF_SCRP = OFF_SCRW + (size_t)NPW * NPIX * 16;          // int2 {corner pixel, smem offset}
   static constexpr size_t OFF_BAR = OFF_SCRP + (size_t)NPW * NPIX * 8;
   static constexpr size_t OFF_SEG = OFF_BAR + (size_t)(4 * NSLAB + 4 * NAP) * 8;
   static constexpr size_t OFF_ACNT = OFF_SEG + MAXSEG * 32 + 64;                  // consumer arrivals per c1 pair slot
-  static constexpr size_t SMEM_BYTES = OFF_ACNT + NAP * 4;
+  static constexpr size_t OFF_DESC = (OFF_ACNT + NAP * 4 + 15) / 16 * 16;            // per compute warp: 32 x {offset, pixels}
+  static constexpr size_t OFF_SBAR = OFF_DESC + (size_t)NCWG * 32 * 16;              // staging full / free barriers
+  static constexpr size_t SMEM_BYTES = OFF_SBAR + 2 * NCWG * 8;
   static_assert(SMEM_BYTES <= SMEM_LIMIT, "shared memory budget");
   static_assert(KV % LPP == 0 && KV % KP == 0 && NAP % 2 == 0, "channel split / ring");
 };
@@ -123,7 +141,7 @@ struct Params {
 
 // ---- event trace (diagnostics, stream_debug bit 16): CTA 0 records (clock << 16 | code << 12 | value) per warp ----
 constexpr int TRACE_LEN = 512;
-__device__ unsigned long long g_trace[NCW + NPW][TRACE_LEN];
+__device__ unsigned long long g_trace[16][TRACE_LEN];
 #define PWC_TR(code, val)                                                                              \
   do {                                                                                                 \
     if ((P.dbg & 16) && blockIdx.x == 0 && lane == 0 && tr_n < TRACE_LEN)                              \
@@ -153,6 +171,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(a), "r"(parity)
         : "memory");
   } while (!done);
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {  // non-blocking
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
 }
 // TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -300,7 +329,7 @@ __device__ __forceinline__ void gather_slab(const T* __restrict__ c2, const Para
   // LPP lanes per pixel, KQ channel chunks per lane
   constexpr int PPI = 32 / G::LPP;               // pixels per warp iteration
   constexpr int NITEMS = G::NPIX * G::KQ / PPI;  // per-lane items of the slab
-  constexpr int GD = HAS_FLOW ? PWC_STREAM_GD : 6;  // items in flight ahead of the one being blended
+  constexpr int GD = HAS_FLOW ? PWC_STREAM_GD : (G::NSW ? 4 : 6);  // items in flight ahead of the one being blended
   static_assert((G::NPIX * G::KQ) % PPI == 0 && NITEMS > GD, "gather items");
   constexpr int CELT = G::KV * 4;                // channels (compile-time: corner offsets become immediates)
   constexpr bool HALF = ElemTraits<T>::kIsHalf;
@@ -438,7 +467,7 @@ __device__ __forceinline__ void correlate(const ulonglong2* __restrict__ ap, con
 }
 
 template <int KV, int NXG, int PXL, bool HAS_FLOW, bool ATMA, typename T, typename TF>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(32 * ((PXL <= 4 ? 12 : 8) + NPW + (PXL <= 6 ? PWC_STREAM_NSW : 0)), 1)
 fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* __restrict__ flow,
                   T* __restrict__ out, const Params P) {
   using G = Geo<KV, NXG, PXL>;
@@ -457,6 +486,8 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
   Seg* segs = reinterpret_cast<Seg*>(smem + G::OFF_SEG);
   int* s_misc = reinterpret_cast<int*>(smem + G::OFF_SEG + MAXSEG * 32);  // [0] nseg, [1] total tasks, [2] task counter, [3] pairs
   int* a_cnt = reinterpret_cast<int*>(smem + G::OFF_ACNT);
+  int4* sdesc = reinterpret_cast<int4*>(smem + G::OFF_DESC);       // {offset lo, offset hi, pixels in range, kind}
+  uint64_t* sbar = reinterpret_cast<uint64_t*>(smem + G::OFF_SBAR);  // [cw] full, [G::NCWG + cw] free
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int tr_n = 0;
@@ -464,6 +495,7 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
   if (tid == 0) {
     for (int i = 0; i < NBB; ++i) { mbar_init(&fullB[i], 32); mbar_init(&emptyB[i], G::EMPTYB_COUNT); }
     for (int i = 0; i < NBA; ++i) { mbar_init(&fullA[i], ATMA ? 1 : 32); mbar_init(&emptyA[i], 6); }
+    for (int i = 0; i < 2 * G::NCWG; ++i) mbar_init(&sbar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the async (TMA) proxy
     // this CTA's contiguous range of (strip, pair) units, cut into per-strip segments
     const long long qlo = P.Q * blockIdx.x / gridDim.x, qhi = P.Q * (blockIdx.x + 1) / gridDim.x;
@@ -491,10 +523,67 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
   __syncthreads();
   const int nseg = s_misc[0];
 
-  if (warp >= NCW) {
+  if (G::NSW > 0 && warp >= G::NCWG + NPW) {
+    // =========================== store warps ===========================
+    // Store warp w serves compute warps w and w + NSW: waits for a staged task, reads the 9-channel runs back in store
+    // order (consecutive lanes = consecutive addresses inside a run) and writes them out.
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G::REGS_STORE));
+    const int sw = warp - G::NCWG - NPW;
+    uint32_t par[2] = {0, 0};
+    bool done[2] = {false, false};
+    while (!(done[0] && done[1])) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (done[h]) continue;
+        const int cw = sw + h * G::NSW;
+        if (!mbar_test(&sbar[cw], par[h])) continue;
+        par[h] ^= 1;
+        const int4* dsc = sdesc + cw * 32;
+        if (dsc[0].w != 0) { done[h] = true; continue; }   // the compute warp has left its task loop
+        PWC_TR(12, cw);
+        const float* stage = sStage + cw * G::STAGE_WORDS;
+        T* optr[9];
+        int nv[9];
+        bool all_full = true;
+#pragma unroll
+        for (int it = 0; it < 9; ++it) {
+          const int idx = it * 32 + lane;
+          const int l2 = idx / 9, w = idx - l2 * 9;
+          const int4 dd = dsc[l2];
+          nv[it] = dd.z;
+          optr[it] = out + (((long long)dd.y << 32) | (unsigned)dd.x) + w;
+          all_full = all_full && (dd.z == 0 || dd.z >= G::PX);
+        }
+        all_full = __all_sync(0xffffffffu, all_full);
+        if (!(P.dbg & 4)) {
+#pragma unroll
+          for (int p = 0; p < G::PX; ++p) {
+            float v[9];
+#pragma unroll
+            for (int it = 0; it < 9; ++it) v[it] = stage[p * 320 + it * 32 + lane];
+            if (all_full) {
+#pragma unroll
+              for (int it = 0; it < 9; ++it)
+                if (nv[it] > 0) optr[it][p * D] = ElemTraits<T>::from_f(v[it]);
+            } else {
+#pragma unroll
+              for (int it = 0; it < 9; ++it)
+                if (p < nv[it]) optr[it][p * D] = ElemTraits<T>::from_f(v[it]);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sbar[G::NCWG + cw]);  // staging buffer and descriptor are free again
+        PWC_TR(13, cw);
+      }
+    }
+    return;
+  }
+
+  if (warp >= G::NCWG) {
     // =========================== producers ===========================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G::REGS_PRODUCER));
-    const int pwarp = warp - NCW;
+    const int pwarp = warp - G::NCWG;
     float4* wsc = reinterpret_cast<float4*>(smem + G::OFF_SCRW) + pwarp * G::NPIX;
     int2* psc = reinterpret_cast<int2*>(smem + G::OFF_SCRP) + pwarp * G::NPIX;
     const float inv_c = 1.0f / (float)P.C;
@@ -555,6 +644,7 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
   float* stage = sStage + warp * G::STAGE_WORDS;
   const int total_tasks = s_misc[1];
   const int lo = lane & 1;
+  uint32_t spar = 0;  // phase of this warp's staging-free barrier
   while (true) {
     int t = 0;
     if (lane == 0) t = atomicAdd(&s_misc[2], 1);
@@ -639,19 +729,7 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
     const bool writer = store && kv0 == 0;
     const long long my_off = writer ? (long long)((((size_t)sg.b * P.H + ya) * P.W + xb) * D + dyi * ND) : 0;
     const int my_nv = writer ? P.W - xb : 0;
-    T* optr[9];
-    int nv[9];
-#pragma unroll
-    for (int it = 0; it < 9; ++it) {
-      const int idx = it * 32 + lane;
-      const int l2 = idx / 9, w = idx - l2 * 9;
-      const long long o = __shfl_sync(0xffffffffu, my_off, l2);
-      nv[it] = __shfl_sync(0xffffffffu, my_nv, l2);
-      optr[it] = out + o + w;
-    }
-    // software pipeline over the pixels: pixel p + 1 is staged while pixel p is read back and stored
-    auto stage_pixel = [&](int p) {
-      float* stg = stage + (p & 1) * (G::STAGE_WORDS / 2);
+    auto stage_pixel = [&](int p, float* stg) {
 #pragma unroll
       for (int d = 0; d < ND; ++d) {
         const float2 h = unpack2(acc[p][d]);
@@ -663,18 +741,82 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
         stg[lane * 9 + d] = fmaxf(0.1f * v, v);
       }
     };
-    stage_pixel(0);
-    __syncwarp();
+    if constexpr (G::FULLSTAGE && G::NSW > 0) {
+      // hand the task to the store warp: wait until it has drained this warp's previous task, publish where the
+      // runs go, stage all pixels, signal
+      mbar_wait(&sbar[G::NCWG + warp], spar ^ 1);
+      spar ^= 1;
+      sdesc[warp * 32 + lane] = make_int4((int)(unsigned)(my_off & 0xffffffffll), (int)(my_off >> 32), my_nv, 0);
 #pragma unroll
-    for (int p = 0; p < G::PX; ++p) {
-      if (p + 1 < G::PX) stage_pixel(p + 1);
-      const float* stg = stage + (p & 1) * (G::STAGE_WORDS / 2);
-#pragma unroll
-      for (int it = 0; it < 9; ++it)
-        if (p < nv[it] && !(P.dbg & 4)) optr[it][p * D] = ElemTraits<T>::from_f(stg[it * 32 + lane]);
+      for (int p = 0; p < G::PX; ++p) stage_pixel(p, stage + p * 320);
       __syncwarp();
+      if (lane == 0) mbar_arrive(&sbar[warp]);
+    } else if constexpr (G::FULLSTAGE) {
+      // every pixel is staged, then one warp sync, then all stores: no serial stage -> sync -> store chain per pixel
+      T* optr[9];
+      int nv[9];
+#pragma unroll
+      for (int it = 0; it < 9; ++it) {
+        const int idx = it * 32 + lane;
+        const int l2 = idx / 9, w = idx - l2 * 9;
+        const long long o = __shfl_sync(0xffffffffu, my_off, l2);
+        nv[it] = __shfl_sync(0xffffffffu, my_nv, l2);
+        optr[it] = out + o + w;
+      }
+#pragma unroll
+      for (int p = 0; p < G::PX; ++p) stage_pixel(p, stage + p * 320);
+      __syncwarp();
+      // nv == 0 marks a lane without output; with all_full every other lane has all PX pixels inside the image
+      const bool all_full = __all_sync(0xffffffffu, my_nv >= G::PX || !writer);
+      if (!(P.dbg & 4)) {
+#pragma unroll
+        for (int p = 0; p < G::PX; ++p) {
+          float v[9];
+#pragma unroll
+          for (int it = 0; it < 9; ++it) v[it] = stage[p * 320 + it * 32 + lane];  // unconditional: the buffer is ours
+          if (all_full) {
+#pragma unroll
+            for (int it = 0; it < 9; ++it)
+              if (nv[it] > 0) optr[it][p * D] = ElemTraits<T>::from_f(v[it]);
+          } else {
+#pragma unroll
+            for (int it = 0; it < 9; ++it)
+              if (p < nv[it]) optr[it][p * D] = ElemTraits<T>::from_f(v[it]);
+          }
+        }
+      }
+      __syncwarp();
+    } else {
+      T* optr[9];
+      int nv[9];
+#pragma unroll
+    for (int it = 0; it < 9; ++it) {
+      const int idx = it * 32 + lane;
+      const int l2 = idx / 9, w = idx - l2 * 9;
+      const long long o = __shfl_sync(0xffffffffu, my_off, l2);
+      nv[it] = __shfl_sync(0xffffffffu, my_nv, l2);
+      optr[it] = out + o + w;
+    }
+      // software pipeline over the pixels: pixel p + 1 is staged while pixel p is read back and stored
+      stage_pixel(0, stage);
+      __syncwarp();
+#pragma unroll
+      for (int p = 0; p < G::PX; ++p) {
+        if (p + 1 < G::PX) stage_pixel(p + 1, stage + ((p + 1) & 1) * 320);
+        const float* stg = stage + (p & 1) * 320;
+#pragma unroll
+        for (int it = 0; it < 9; ++it)
+          if (p < nv[it] && !(P.dbg & 4)) optr[it][p * D] = ElemTraits<T>::from_f(stg[it * 32 + lane]);
+        __syncwarp();
+      }
     }
     PWC_TR(11, t);
+  }
+  if constexpr (G::FULLSTAGE && G::NSW > 0) {  // tell the store warp that this compute warp is done
+    mbar_wait(&sbar[G::NCWG + warp], spar ^ 1);
+    sdesc[warp * 32 + lane] = make_int4(0, 0, 0, 1);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sbar[warp]);
   }
 }
 
@@ -699,7 +841,7 @@ int launch_cfg(const T* c1, const T* c2, const TF* flow, float flow_scale, T* ou
   auto go = [&](auto kern) -> int {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BYTES) != cudaSuccess)
       return -1;
-    kern<<<(unsigned)grid, NTHREADS, G::SMEM_BYTES, st>>>(c1, c2, flow, out, P);
+    kern<<<(unsigned)grid, G::NTHREADS, G::SMEM_BYTES, st>>>(c1, c2, flow, out, P);
     return 0;
   };
   // TMA needs 16-byte aligned global rows: C % 4 == 0 and an aligned base (checked by the caller)
@@ -720,9 +862,9 @@ int launch(const T* c1, const T* c2, const TF* flow, float flow_scale, T* out, i
 #define PWC_STREAM_GO(KV, NXG, PXL) \
   return launch_cfg<KV, NXG, PXL, T, TF>(c1, c2, flow, flow_scale, out, B, H, W, C, st, sms, ctas_override, pf_dist, dbg)
   switch (C) {
-    case 16: PWC_STREAM_GO(4, 4, PWC_STREAM_PX32);
+    case 16: PWC_STREAM_GO(4, 4, 6);
     case 32: PWC_STREAM_GO(8, 4, PWC_STREAM_PX32);
-    case 64: PWC_STREAM_GO(16, 2, PWC_STREAM_PX32);
+    case 64: PWC_STREAM_GO(16, 2, 6);
     case 96: PWC_STREAM_GO(24, 1, 8);
     case 128: PWC_STREAM_GO(32, 1, 8);
     default: return 1;

@@ -115,6 +115,14 @@ int fwd_typed(const void* c1, const void* c2, const void* flow, float flow_scale
   // auto: the streaming kernel wins on tall levels (it pays ~5 warm-up slabs per strip segment), the tiled kernel
   // on short ones; measured crossover between H = 28 and H = 56 (profiles/r01_notes.md)
   if (impl == 0) impl = !tuned_ok ? 1 : (H >= 40 ? 3 : 2);
+  // un-warped small level (the pyramid top): too few tiles for the tiled kernel, one thread per output element wins
+  if (g_fwd_impl.load() == 0 && flow == nullptr && vec_ok && (int64_t)B * H * W <= 16384) {
+    const int64_t total = (int64_t)B * H * W * D;
+    pwc::fwd_noflow_vec4_kernel<T><<<grid_for(total, 256, dev.sms), 256, 0, st>>>((const T*)c1, (const T*)c2, (T*)out, B, H,
+                                                                                W, C, r, ops);
+    PWC_LAUNCH_CHECK();
+    return PWC_OK;
+  }
   if (impl >= 2 && !tuned_ok) impl = 1;
 #ifdef PWC_HAVE_STREAM_KERNEL
   if (impl == 3) {
@@ -531,40 +539,57 @@ int pwc_pyramid_fwd_host(pwc_host_ctx* c, const pwc_level_t* lv, int n_levels, i
   if (!dtype_ok(dtype) || !dtype_ok(flow_dtype)) return fail(PWC_ERR_BAD_DTYPE, "unknown dtype");
   const size_t es = elt_size(dtype), fs = elt_size(flow_dtype);
   const int64_t D = (int64_t)(2 * r + 1) * (2 * r + 1);
-  while ((int)c->ev_in.size() < n_levels) {
+  // The batch is cut into chunks (batch elements are independent) so that the upload of chunk k+1, the
+  // kernels of chunk k and the download of chunk k-1 overlap: PCIe is full duplex and the copies, not the kernels,
+  // bound this path (822 MB per step at the headline workload against < 1 ms of kernels).
+  const int nch = B >= 8 ? 8 : (B > 0 ? B : 1);
+  const int cb = (B + nch - 1) / nch;
+  while ((int)c->ev_in.size() < n_levels * nch) {
     cudaEvent_t e1, e2;
     PWC_CUDA(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
     PWC_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
     c->ev_in.push_back(e1);
     c->ev_run.push_back(e2);
   }
-  // largest level first so the copy engines and the SMs overlap for longest
   for (int i = 0; i < n_levels; ++i) {
     const pwc_level_t& L = lv[i];
     int rc = check_shape(B, L.H, L.W, L.C, r, L.flow != nullptr);
     if (rc) return rc;
     const size_t npix = (size_t)B * L.H * L.W;
     const int64_t ops = L.out_pixel_stride ? L.out_pixel_stride : D;
-    const size_t nb_feat = npix * L.C * es, nb_flow = npix * 2 * fs, nb_out = npix * ops * es;
-    if ((rc = ctx_reserve(c, 4 * i + 0, nb_feat))) return rc;
-    if ((rc = ctx_reserve(c, 4 * i + 1, nb_feat))) return rc;
-    if (L.flow && (rc = ctx_reserve(c, 4 * i + 2, nb_flow))) return rc;
-    if ((rc = ctx_reserve(c, 4 * i + 3, nb_out))) return rc;
-    void* d_c1 = c->bufs[4 * i + 0].p;
-    void* d_c2 = c->bufs[4 * i + 1].p;
-    void* d_fl = L.flow ? c->bufs[4 * i + 2].p : nullptr;
-    void* d_out = c->bufs[4 * i + 3].p;
-    if (npix == 0) continue;
-    PWC_CUDA(cudaMemcpyAsync(d_c1, L.c1, nb_feat, cudaMemcpyHostToDevice, c->s_in));
-    PWC_CUDA(cudaMemcpyAsync(d_c2, L.c2, nb_feat, cudaMemcpyHostToDevice, c->s_in));
-    if (L.flow) PWC_CUDA(cudaMemcpyAsync(d_fl, L.flow, nb_flow, cudaMemcpyHostToDevice, c->s_in));
-    PWC_CUDA(cudaEventRecord(c->ev_in[i], c->s_in));
-    PWC_CUDA(cudaStreamWaitEvent(c->s_run, c->ev_in[i], 0));
-    rc = fwd_entry(d_c1, d_c2, d_fl, L.flow_scale, d_out, B, L.H, L.W, L.C, r, dtype, flow_dtype, ops, c->s_run);
-    if (rc) return rc;
-    PWC_CUDA(cudaEventRecord(c->ev_run[i], c->s_run));
-    PWC_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_run[i], 0));
-    PWC_CUDA(cudaMemcpyAsync(L.out, d_out, nb_out, cudaMemcpyDeviceToHost, c->s_out));
+    if ((rc = ctx_reserve(c, 4 * i + 0, npix * L.C * es))) return rc;
+    if ((rc = ctx_reserve(c, 4 * i + 1, npix * L.C * es))) return rc;
+    if (L.flow && (rc = ctx_reserve(c, 4 * i + 2, npix * 2 * fs))) return rc;
+    if ((rc = ctx_reserve(c, 4 * i + 3, npix * ops * es))) return rc;
+  }
+  for (int ch = 0; ch < nch; ++ch) {
+    const int b0 = ch * cb, bn = (b0 + cb <= B ? cb : B - b0);
+    if (bn <= 0) break;
+    for (int i = 0; i < n_levels; ++i) {
+      const pwc_level_t& L = lv[i];
+      const size_t pix0 = (size_t)b0 * L.H * L.W, npix = (size_t)bn * L.H * L.W;
+      if (npix == 0) continue;
+      const int64_t ops = L.out_pixel_stride ? L.out_pixel_stride : D;
+      const size_t o_feat = pix0 * L.C * es, nb_feat = npix * L.C * es;
+      const size_t o_flow = pix0 * 2 * fs, nb_flow = npix * 2 * fs;
+      const size_t o_out = pix0 * ops * es, nb_out = npix * ops * es;
+      char* d_c1 = (char*)c->bufs[4 * i + 0].p + o_feat;
+      char* d_c2 = (char*)c->bufs[4 * i + 1].p + o_feat;
+      char* d_fl = L.flow ? (char*)c->bufs[4 * i + 2].p + o_flow : nullptr;
+      char* d_out = (char*)c->bufs[4 * i + 3].p + o_out;
+      const int e = ch * n_levels + i;
+      PWC_CUDA(cudaMemcpyAsync(d_c1, (const char*)L.c1 + o_feat, nb_feat, cudaMemcpyHostToDevice, c->s_in));
+      PWC_CUDA(cudaMemcpyAsync(d_c2, (const char*)L.c2 + o_feat, nb_feat, cudaMemcpyHostToDevice, c->s_in));
+      if (L.flow)
+        PWC_CUDA(cudaMemcpyAsync(d_fl, (const char*)L.flow + o_flow, nb_flow, cudaMemcpyHostToDevice, c->s_in));
+      PWC_CUDA(cudaEventRecord(c->ev_in[e], c->s_in));
+      PWC_CUDA(cudaStreamWaitEvent(c->s_run, c->ev_in[e], 0));
+      int rc = fwd_entry(d_c1, d_c2, d_fl, L.flow_scale, d_out, bn, L.H, L.W, L.C, r, dtype, flow_dtype, ops, c->s_run);
+      if (rc) return rc;
+      PWC_CUDA(cudaEventRecord(c->ev_run[e], c->s_run));
+      PWC_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_run[e], 0));
+      PWC_CUDA(cudaMemcpyAsync((char*)L.out + o_out, d_out, nb_out, cudaMemcpyDeviceToHost, c->s_out));
+    }
   }
   PWC_CUDA(cudaStreamSynchronize(c->s_out));
   PWC_CUDA(cudaStreamSynchronize(c->s_in));
