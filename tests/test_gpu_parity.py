@@ -211,17 +211,19 @@ def test_zero_flow_backward_tie_rule(dev):
 
 
 def test_out_slice_of_concat_buffer(dev):
-    # model_pwcnet.py:1424 concatenates [corr, c1, up_flow, up_feat]; write corr straight into its slice
-    d = synth.make_level(2, 14, 32, 128, 400, np.float32, "smooth")
-    buf = torch.full((2, 14, 32, 81 + 128 + 2), -7.0, device=dev)
-    c1, c2, flow = (to_dev(d[k], dev) for k in ("c1", "c2", "flow"))
-    for impl in IMPLS:
-        buf.fill_(-7.0)
-        _ffi.set_option("fwd_impl", impl)
-        cost_volume(c1, dense_image_warp(c2, flow), 4, "corr5", out=buf[..., :81])
+    # model_pwcnet.py:1424 concatenates [corr, c1, up_flow, up_feat]; write corr straight into its slice.
+    # Second shape: a tall 32-channel level, i.e. the streaming kernel's 6-pixel geometry with a strided output.
+    for (b, h, w, c, seed) in ((2, 14, 32, 128, 400), (2, 44, 70, 32, 401)):
+        d = synth.make_level(b, h, w, c, seed, np.float32, "smooth")
+        buf = torch.full((b, h, w, 81 + c + 2), -7.0, device=dev)
+        c1, c2, flow = (to_dev(d[k], dev) for k in ("c1", "c2", "flow"))
         ref = O.warp_cost_volume(d["c1"], d["c2"], d["flow"], 4)
-        assert_close(buf[..., :81].cpu().numpy(), ref, 1e-5, "slice")
-        assert torch.all(buf[..., 81:] == -7.0)
+        for impl in IMPLS:
+            buf.fill_(-7.0)
+            _ffi.set_option("fwd_impl", impl)
+            cost_volume(c1, dense_image_warp(c2, flow), 4, "corr5", out=buf[..., :81])
+            assert_close(buf[..., :81].cpu().numpy(), ref, 1e-5, f"slice impl {impl}")
+            assert torch.all(buf[..., 81:] == -7.0)
 
 
 def test_non_contiguous_and_dlpack_inputs(dev):

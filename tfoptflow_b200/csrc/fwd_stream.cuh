@@ -564,11 +564,11 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
             if (all_full) {
 #pragma unroll
               for (int it = 0; it < 9; ++it)
-                if (nv[it] > 0) optr[it][p * D] = ElemTraits<T>::from_f(v[it]);
+                if (nv[it] > 0) optr[it][(size_t)p * P.ops] = ElemTraits<T>::from_f(v[it]);
             } else {
 #pragma unroll
               for (int it = 0; it < 9; ++it)
-                if (p < nv[it]) optr[it][p * D] = ElemTraits<T>::from_f(v[it]);
+                if (p < nv[it]) optr[it][(size_t)p * P.ops] = ElemTraits<T>::from_f(v[it]);
             }
           }
         }
@@ -727,7 +727,7 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
     const int xb = sg.x0 + xg * G::PX;
     const int dyi = yb - ya + R;
     const bool writer = store && kv0 == 0;
-    const long long my_off = writer ? (long long)((((size_t)sg.b * P.H + ya) * P.W + xb) * D + dyi * ND) : 0;
+    const long long my_off = writer ? (long long)((((size_t)sg.b * P.H + ya) * P.W + xb) * P.ops + dyi * ND) : 0;
     const int my_nv = writer ? P.W - xb : 0;
     auto stage_pixel = [&](int p, float* stg) {
 #pragma unroll
@@ -777,11 +777,11 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
           if (all_full) {
 #pragma unroll
             for (int it = 0; it < 9; ++it)
-              if (nv[it] > 0) optr[it][p * D] = ElemTraits<T>::from_f(v[it]);
+              if (nv[it] > 0) optr[it][(size_t)p * P.ops] = ElemTraits<T>::from_f(v[it]);
           } else {
 #pragma unroll
             for (int it = 0; it < 9; ++it)
-              if (p < nv[it]) optr[it][p * D] = ElemTraits<T>::from_f(v[it]);
+              if (p < nv[it]) optr[it][(size_t)p * P.ops] = ElemTraits<T>::from_f(v[it]);
           }
         }
       }
@@ -806,7 +806,7 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
         const float* stg = stage + (p & 1) * 320;
 #pragma unroll
         for (int it = 0; it < 9; ++it)
-          if (p < nv[it] && !(P.dbg & 4)) optr[it][p * D] = ElemTraits<T>::from_f(stg[it * 32 + lane]);
+          if (p < nv[it] && !(P.dbg & 4)) optr[it][(size_t)p * P.ops] = ElemTraits<T>::from_f(stg[it * 32 + lane]);
         __syncwarp();
       }
     }
@@ -823,10 +823,10 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
 // Host-side launcher.  Returns 0 when launched, 1 when the shape is not covered, -1 on a CUDA error.
 template <int KV, int NXG, int PXL, typename T, typename TF>
 int launch_cfg(const T* c1, const T* c2, const TF* flow, float flow_scale, T* out, int B, int H, int W, int C,
-               cudaStream_t st, int sms, int ctas_override, int pf_dist, int dbg) {
+               int64_t ops, cudaStream_t st, int sms, int ctas_override, int pf_dist, int dbg) {
   using G = Geo<KV, NXG, PXL>;
   Params P;
-  P.B = B; P.H = H; P.W = W; P.C = C; P.ops = D; P.flow_scale = flow_scale;
+  P.B = B; P.H = H; P.W = W; P.C = C; P.ops = ops; P.flow_scale = flow_scale;
   P.NPAIR = (H + 1) / 2;
   P.nstrip_x = (W + G::TW - 1) / G::TW;
   P.Q = (long long)B * P.nstrip_x * P.NPAIR;
@@ -854,13 +854,14 @@ int launch_cfg(const T* c1, const T* c2, const TF* flow, float flow_scale, T* ou
                          : go(fwd_stream_kernel<KV, NXG, PXL, false, false, T, TF>);
 }
 
-// Covered: dense output (pixel stride 81), C in {16, 32, 64, 96, 128}.  Everything else returns 1 (caller falls back).
+// Covered: any output pixel stride >= 81 (a channel slice of the concat buffer, model_pwcnet.py:1424),
+// C in {16, 32, 64, 96, 128}.  Everything else returns 1 (caller falls back).
 template <typename T, typename TF>
 int launch(const T* c1, const T* c2, const TF* flow, float flow_scale, T* out, int B, int H, int W, int C,
            int64_t ops, cudaStream_t st, int sms, int ctas_override, int pf_dist, int dbg = 0) {
-  if (ops != D) return 1;
+  if (ops < D) return 1;
 #define PWC_STREAM_GO(KV, NXG, PXL) \
-  return launch_cfg<KV, NXG, PXL, T, TF>(c1, c2, flow, flow_scale, out, B, H, W, C, st, sms, ctas_override, pf_dist, dbg)
+  return launch_cfg<KV, NXG, PXL, T, TF>(c1, c2, flow, flow_scale, out, B, H, W, C, ops, st, sms, ctas_override, pf_dist, dbg)
   switch (C) {
     case 16: PWC_STREAM_GO(4, 4, 6);
     case 32: PWC_STREAM_GO(8, 4, PWC_STREAM_PX32);
