@@ -34,7 +34,7 @@ def run_cta(B, H, W, NXG, grid, cta, written, slab_arr, pair_arr, PX=8):
     return segs
 
 
-@pytest.mark.parametrize("NXG,PX", [(4, 8), (4, 6), (4, 4), (2, 6), (2, 8), (1, 8)])
+@pytest.mark.parametrize("NXG,PX", [(4, 8), (4, 6), (4, 4), (2, 6), (2, 8), (1, 8), (1, 6)])
 @pytest.mark.parametrize("B,H,W,grid", [(2, 12, 40, 3), (1, 7, 33, 5), (3, 10, 64, 7), (1, 112, 32, 4), (2, 5, 8, 1),
                                         (1, 2, 2, 1), (4, 6, 70, 11)])
 def test_stream_schedule_covers_every_output_once(B, H, W, grid, NXG, PX):

@@ -52,6 +52,12 @@ constexpr size_t SMEM_LIMIT = 232448;
 #ifndef PWC_STREAM_GD
 #define PWC_STREAM_GD 3
 #endif
+#ifndef PWC_STREAM_NXG96
+#define PWC_STREAM_NXG96 2
+#endif
+#ifndef PWC_STREAM_NXG128
+#define PWC_STREAM_NXG128 2
+#endif
 #ifndef PWC_STREAM_NSW
 #define PWC_STREAM_NSW 0
 #endif
@@ -60,24 +66,31 @@ constexpr size_t SMEM_LIMIT = 232448;
 #endif
 
 constexpr int pad_to(int v, int r) { return v + ((r - v % 8) + 8) % 8; }  // smallest v' >= v with v' % 8 == r
+constexpr int pad_to16(int v, int r) { return v + ((r - v % 16) + 16) % 16; }
 
 // PX = pixels per lane-task (8, or 6 where the 72 packed accumulators of 8 pixels leave ptxas no room for a clean
 // rolled channel loop: 54 pairs + operands fit 184 registers and give the producers 136)
-template <int KV_, int NXG_, int PX_ = 8>
+// AB = bytes per (pixel, channel quad) in the c1 ring: 16 (fp32) or 8 (raw 16-bit elements delivered by TMA and widened
+// in the correlation loop)
+template <int KV_, int NXG_, int PX_ = 8, int AB_ = 16>
 struct Geo {
-  static constexpr int KV = KV_, NXG = NXG_, PX = PX_;
+  static constexpr int KV = KV_, NXG = NXG_, PX = PX_, AB = AB_;
   static constexpr int TW = PX * NXG;                 // strip width
   static constexpr int BU = TW + 2 * R;               // warped pixels per row (with halo)
   static constexpr int NPIX = 2 * BU;                 // pixels per slab
   // float4 units.  c1 pair slot: [sub(2)][xg][p(8)][kv] ; warped slab slot: [bsel(2)][u(BU)][kv], 2 pads per 8 pixels
-  static constexpr int AXG = pad_to(PX * KV, 4);
-  static constexpr int AROW = pad_to(NXG * AXG, 1);
+  // c1 strides in units of AB bytes.  16-byte units: row 1, pair slot 2, x-group 4 (mod 8 = one 128-byte bank window).
+  // 8-byte units (16-bit c1): everything even (TMA wants 16-byte destinations): row 2, slot 4, x-group 8 (mod 16).
+  static constexpr int AXG = AB == 16 ? pad_to(PX * KV, 4) : pad_to16(PX * KV, 8);
+  static constexpr int AROW = AB == 16 ? pad_to(NXG * AXG, 1) : pad_to16(NXG * AXG, 2);
   static constexpr int ASLOT = 2 * AROW;
   static constexpr int BXPAD = 2;
   static constexpr int BXG = PX * KV + BXPAD;
   static constexpr int BROW = pad_to(BU * KV + ((BU + PX - 1) / PX) * BXPAD, 1);
   static constexpr int BSLOT = 2 * BROW;
-  static_assert(AXG % 8 == 4 && AROW % 8 == 1 && ASLOT % 8 == 2 && BROW % 8 == 1, "bank-group strides");
+  static_assert(AB == 8 || (AXG % 8 == 4 && AROW % 8 == 1 && ASLOT % 8 == 2), "c1 bank-group strides");
+  static_assert(AB == 16 || (AXG % 16 == 8 && AROW % 16 == 2 && ASLOT % 16 == 4), "16-bit c1 strides");
+  static_assert(BROW % 8 == 1, "warped-row stride");
   static constexpr int NH = 16 / NXG;                 // c1 rows (hi values) per full task
   static constexpr int NF = 8 * GS / NH;              // full tasks per group: 8 / 4 / 2
   static constexpr int TPG = NF + 1;                  // + one edge task
@@ -101,15 +114,15 @@ struct Geo {
   static constexpr int EMPTYB_COUNT = (NXG == 4 ? 2 : 1) + 1;
   static constexpr int LPP = KV >= 8 ? 8 : KV;        // producer lanes per pixel
   static constexpr int KQ = KV / LPP;                 // kv chunks per lane
-  static constexpr int NSLAB = PX <= 4 ? 10 : KV == 32 ? 6 : (KV == 16 ? (PX <= 6 ? 8 : 6) : (KV == 8 ? PWC_STREAM_NSLAB8 : 7));
-  static constexpr int NAP = PX <= 4 ? 14 : KV == 32 ? 10 : (KV == 8 ? PWC_STREAM_NAP8 : 12);     // even: the wrap-around keeps consecutive pairs 2 bank groups apart
+  static constexpr int NSLAB = PX <= 4 ? 10 : (KV == 32 && NXG == 2) ? 4 : (KV == 24 && NXG == 2) ? 6 : KV == 32 ? 6 : (KV == 16 ? (PX <= 6 ? 8 : 6) : (KV == 8 ? PWC_STREAM_NSLAB8 : 7));
+  static constexpr int NAP = PX <= 4 ? 14 : (KV == 32 && NXG == 2) ? 8 : (KV == 24 && NXG == 2) ? 10 : KV == 32 ? 12 : (KV == 8 ? PWC_STREAM_NAP8 : 12);     // even: the wrap-around keeps consecutive pairs 2 bank groups apart
   // transposition buffer per compute warp: all PX pixels at once where shared memory allows (one warp sync per task),
   // else two pixels, double buffered
-  static constexpr bool FULLSTAGE = PX <= 6;
+  static constexpr bool FULLSTAGE = PX <= 6 && KV <= 16;
   static constexpr int STAGE_WORDS = FULLSTAGE ? 320 * PX : 640;
   static constexpr size_t OFF_B = 0;
   static constexpr size_t OFF_A = OFF_B + (size_t)NSLAB * BSLOT * 16;
-  static constexpr size_t OFF_STAGE = OFF_A + (size_t)NAP * ASLOT * 16;
+  static constexpr size_t OFF_STAGE = (OFF_A + (size_t)NAP * ASLOT * AB + 15) / 16 * 16;
   static constexpr size_t OFF_SCRW = OFF_STAGE + (size_t)NCWG * STAGE_WORDS * 4;   // float4 weights per pixel
   static constexpr size_t OFF_SCRP = OFF_SCRW + (size_t)NPW * NPIX * 16;          // int2 {corner pixel, smem offset}
   static constexpr size_t OFF_BAR = OFF_SCRP + (size_t)NPW * NPIX * 8;
@@ -250,44 +263,26 @@ __device__ __forceinline__ void prefetch_rows(const T* c2, const TF* flow, const
   }
 }
 
-// c1 rows 2k, 2k+1 of the strip by TMA: one bulk copy per (row, 8-pixel group), i.e. 1 KB at C = 32
-template <typename G>
-__device__ __forceinline__ void produce_pair_tma(const float* __restrict__ c1, const Params& P, const Seg& sg, int k,
-                                                 float4* __restrict__ sA_slot, uint64_t* bar, int lane) {
-  if (lane == 0) {
-    const int rows = min(2, P.H - 2 * k), px = min(G::TW, P.W - sg.x0);
-    mbar_arrive_expect_tx(bar, (uint32_t)(rows * px * P.C * 4));
-  }
-  __syncwarp();
-  if (lane < 2 * G::NXG) {
-    const int row = lane / G::NXG, xg = lane % G::NXG;
-    const int y = 2 * k + row, x = sg.x0 + G::PX * xg;
-    if (y < P.H && x < P.W) {
-      const int npx = min(G::PX, P.W - x);
-      bulk_g2s(sA_slot + row * G::AROW + xg * G::AXG, c1 + (((size_t)sg.b * P.H + y) * P.W + x) * P.C,
-               (uint32_t)(npx * P.C * 4), bar);
-    }
-  }
-}
-
-// The same by a single lane, for global pair index `ag` (segment looked up in the table): used by the consumer that
-// frees a slot to refill it at once (credit return: no producer ever waits for c1 space).
-template <typename G>
-__device__ __forceinline__ void refill_pair_tma(const float* __restrict__ c1, const Params& P, const Seg* segs, int nseg,
-                                                int ag, float4* __restrict__ sA, uint64_t* fullA) {
+// c1 pair `ag` (global pair index; segment looked up in the table) by TMA, issued by a single lane: one bulk copy per
+// (row, PX-pixel group), the elements exactly as stored (fp32, or 16-bit widened later by the compute warps).
+// Used for the initial fill and by the consumer that frees a slot (credit return: no producer ever waits for c1 space).
+template <typename G, typename T>
+__device__ __forceinline__ void refill_pair_tma(const T* __restrict__ c1, const Params& P, const Seg* segs, int nseg,
+                                                int ag, unsigned char* __restrict__ sA, uint64_t* fullA) {
+  static_assert(sizeof(T) * 4 == G::AB, "c1 ring element size");
   int si = 0;
   while (si + 1 < nseg && segs[si + 1].a0 <= ag) ++si;
   const int b = segs[si].b, x0 = segs[si].x0, k = segs[si].p0 + (ag - segs[si].a0);
   uint64_t* bar = &fullA[ag % (2 * G::NAP)];
-  float4* slot = sA + (size_t)(ag % G::NAP) * G::ASLOT;
+  unsigned char* slot = sA + (size_t)(ag % G::NAP) * G::ASLOT * G::AB;
   const int rows = min(2, P.H - 2 * k), px = min(G::TW, P.W - x0);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // consumers' generic reads of the slot come first
-  mbar_arrive_expect_tx(bar, (uint32_t)(rows * px * P.C * 4));
+  mbar_arrive_expect_tx(bar, (uint32_t)(rows * px * P.C * (int)sizeof(T)));
   for (int row = 0; row < rows; ++row)
     for (int xg = 0; xg * G::PX < px; ++xg) {
       const int x = x0 + G::PX * xg, npx = min(G::PX, P.W - x);
-      bulk_g2s(slot + row * G::AROW + xg * G::AXG, c1 + (((size_t)b * P.H + 2 * k + row) * P.W + x) * P.C,
-               (uint32_t)(npx * P.C * 4), bar);
+      bulk_g2s(slot + (size_t)(row * G::AROW + xg * G::AXG) * G::AB,
+               c1 + (((size_t)b * P.H + 2 * k + row) * P.W + x) * P.C, (uint32_t)(npx * P.C * (int)sizeof(T)), bar);
     }
 }
 
@@ -432,8 +427,30 @@ __device__ __forceinline__ void slab_coords(const SlabFlow<G, HAS_FLOW, TF>& F, 
 
 // ---- per-lane correlation: 1 row x 8 pixels x 9 dx against ONE warped row, kv in [kv0, kv1) ------------
 // acc[p][d] = (sum over even channel pairs, sum over odd channel pairs) of c1[p] * warped[p + d]
-template <typename G>
-__device__ __forceinline__ void correlate(const ulonglong2* __restrict__ ap, const ulonglong2* __restrict__ bp,
+// 4 channels of c1 at ring position i, widened to two f32x2 operands
+template <typename G, typename T>
+__device__ __forceinline__ ulonglong2 load_a(const unsigned char* __restrict__ ap, int i) {
+  if constexpr (G::AB == 16) {
+    return reinterpret_cast<const ulonglong2*>(ap)[i];
+  } else {
+    const uint2 r = reinterpret_cast<const uint2*>(ap)[i];
+    float2 lo, hi;
+    if constexpr (std::is_same<T, __half>::value) {
+      lo = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+      hi = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+    } else {  // bf16: the upper 16 bits of an fp32
+      lo = make_float2(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u));
+      hi = make_float2(__uint_as_float(r.y << 16), __uint_as_float(r.y & 0xffff0000u));
+    }
+    ulonglong2 o;
+    o.x = pack2(lo.x, lo.y);
+    o.y = pack2(hi.x, hi.y);
+    return o;
+  }
+}
+
+template <typename G, typename T>
+__device__ __forceinline__ void correlate(const unsigned char* __restrict__ ap, const ulonglong2* __restrict__ bp,
                                           int kv0, int kv1, u64 (&acc)[G::PX][ND]) {
   // Unrolled by KU channel quads: with a rolled loop ptxas rotates the 72 accumulator pairs through ~100 MOVs per
   // iteration.  kv1 - kv0 is KV or KV / KP, both multiples of KU.
@@ -446,7 +463,7 @@ __device__ __forceinline__ void correlate(const ulonglong2* __restrict__ ap, con
       const int kv = kvb + ku;
       ulonglong2 a[G::PX];
 #pragma unroll
-      for (int p = 0; p < G::PX; ++p) a[p] = ap[kv + p * G::KV];
+      for (int p = 0; p < G::PX; ++p) a[p] = load_a<G, T>(ap, kv + p * G::KV);
 #pragma unroll
       for (int j = 0; j < G::PX + 2 * R; ++j) {
         const ulonglong2 b = bp[kv + j * G::KV + (j / G::PX) * G::BXPAD];
@@ -470,11 +487,10 @@ template <int KV, int NXG, int PXL, bool HAS_FLOW, bool ATMA, typename T, typena
 __global__ void __launch_bounds__(32 * ((PXL <= 4 ? 12 : 8) + NPW + (PXL <= 6 ? PWC_STREAM_NSW : 0)), 1)
 fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* __restrict__ flow,
                   T* __restrict__ out, const Params P) {
-  using G = Geo<KV, NXG, PXL>;
-  static_assert(!ATMA || std::is_same<T, float>::value, "TMA delivers c1 as stored: fp32 only");
+  using G = Geo<KV, NXG, PXL, ATMA ? (int)sizeof(T) * 4 : 16>;
   extern __shared__ __align__(128) unsigned char smem[];
   float4* sB = reinterpret_cast<float4*>(smem + G::OFF_B);
-  float4* sA = reinterpret_cast<float4*>(smem + G::OFF_A);
+  unsigned char* sA = smem + G::OFF_A;
   float* sStage = reinterpret_cast<float*>(smem + G::OFF_STAGE);
   // Two alternating barrier sets per data slot (index j % 2N, parity (j / 2N) & 1): with one set a waiter that
   // is two uses ahead of a slow producer would pass a parity wait prematurely (tests/stream_protocol_sim.py).
@@ -600,7 +616,7 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
     auto slab_live = [&](int m) { return 2 * m >= 0 && 2 * m - 1 < P.H; };  // else entirely outside the image
     if constexpr (ATMA) {  // initial fill of the c1 ring; afterwards the consumer that frees a slot refills it
       const int npairs = s_misc[3];
-      if (pwarp == 0 && lane < G::NAP && lane < npairs) refill_pair_tma<G>(c1, P, segs, nseg, lane, sA, fullA);
+      if (pwarp == 0 && lane < G::NAP && lane < npairs) refill_pair_tma<G, T>(c1, P, segs, nseg, lane, sA, fullA);
     }
     SlabFlow<G, HAS_FLOW, TF> F;
     advance();
@@ -614,7 +630,8 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
         if (sg.p0 + l < sg.p1) {
           const int ag = sg.a0 + l, slot = ag % G::NAP, prev = ag - G::NAP;
           if (prev >= 0) mbar_wait(&emptyA[prev % NBA], (prev / NBA) & 1);  // previous occupant fully consumed
-          if (!(P.dbg & 2)) produce_pair<G, T>(c1, P, sg, sg.p0 + l, sA + (size_t)slot * G::ASLOT, lane);
+          if (!(P.dbg & 2))
+            produce_pair<G, T>(c1, P, sg, sg.p0 + l, reinterpret_cast<float4*>(sA) + (size_t)slot * G::ASLOT, lane);
           mbar_arrive(&fullA[ag % NBA]);
         }
       }
@@ -702,9 +719,9 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
 #pragma unroll
       for (int d = 0; d < ND; ++d) acc[p][d] = 0ull;
     if (active && !(P.dbg & 1)) {
-      const ulonglong2* ap = reinterpret_cast<const ulonglong2*>(sA + (size_t)sa * G::ASLOT + sub * G::AROW + xg * G::AXG);
+      const unsigned char* ap = sA + ((size_t)sa * G::ASLOT + sub * G::AROW + xg * G::AXG) * G::AB;
       const ulonglong2* bp = reinterpret_cast<const ulonglong2*>(sB + (size_t)sb * G::BSLOT + bsel * G::BROW + xg * G::BXG);
-      correlate<G>(ap, bp, kv0, kv1, acc);
+      correlate<G, T>(ap, bp, kv0, kv1, acc);
     }
     __syncwarp();
     PWC_TR(10, t);
@@ -715,7 +732,7 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
         __threadfence_block();
         if (atomicAdd(&a_cnt[sa], 1) == 5) {  // last of the 6 arrivals: the slot is free, refill it with pair ag + NAP
           a_cnt[sa] = 0;
-          if (ag + G::NAP < s_misc[3]) refill_pair_tma<G>(c1, P, segs, nseg, ag + G::NAP, sA, fullA);
+          if (ag + G::NAP < s_misc[3]) refill_pair_tma<G, T>(c1, P, segs, nseg, ag + G::NAP, sA, fullA);
         }
       } else {
         mbar_arrive(&emptyA[ag % NBA]);
@@ -824,7 +841,7 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
 template <int KV, int NXG, int PXL, typename T, typename TF>
 int launch_cfg(const T* c1, const T* c2, const TF* flow, float flow_scale, T* out, int B, int H, int W, int C,
                int64_t ops, cudaStream_t st, int sms, int ctas_override, int pf_dist, int dbg) {
-  using G = Geo<KV, NXG, PXL>;
+  using G = Geo<KV, NXG, PXL, 16>;  // strip geometry (the c1 ring element size only changes the shared-memory budget)
   Params P;
   P.B = B; P.H = H; P.W = W; P.C = C; P.ops = ops; P.flow_scale = flow_scale;
   P.NPAIR = (H + 1) / 2;
@@ -838,20 +855,21 @@ int launch_cfg(const T* c1, const T* c2, const TF* flow, float flow_scale, T* ou
   // every CTA must fit its range into MAXSEG per-strip segments
   const long long per = (P.Q + grid - 1) / grid;
   if (per / P.NPAIR + 2 > MAXSEG) return 1;
-  auto go = [&](auto kern) -> int {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BYTES) != cudaSuccess)
+  auto go = [&](auto kern, size_t smem_bytes) -> int {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess)
       return -1;
-    kern<<<(unsigned)grid, G::NTHREADS, G::SMEM_BYTES, st>>>(c1, c2, flow, out, P);
+    kern<<<(unsigned)grid, G::NTHREADS, smem_bytes, st>>>(c1, c2, flow, out, P);
     return 0;
   };
-  // TMA needs 16-byte aligned global rows: C % 4 == 0 and an aligned base (checked by the caller)
-  if constexpr (std::is_same<T, float>::value) {
-    if (!(dbg & 8))
-      return flow != nullptr ? go(fwd_stream_kernel<KV, NXG, PXL, true, true, T, TF>)
-                             : go(fwd_stream_kernel<KV, NXG, PXL, false, true, T, TF>);
+  // TMA needs 16-byte aligned global rows: C % 8 == 0 for 16-bit elements, C % 4 == 0 for fp32, and an aligned base
+  // (checked by the caller); stream_debug bit 8 forces the LDG/STS c1 path
+  if (!(dbg & 8) && (C * (int)sizeof(T)) % 16 == 0) {
+    using GT = Geo<KV, NXG, PXL, (int)sizeof(T) * 4>;
+    return flow != nullptr ? go(fwd_stream_kernel<KV, NXG, PXL, true, true, T, TF>, GT::SMEM_BYTES)
+                           : go(fwd_stream_kernel<KV, NXG, PXL, false, true, T, TF>, GT::SMEM_BYTES);
   }
-  return flow != nullptr ? go(fwd_stream_kernel<KV, NXG, PXL, true, false, T, TF>)
-                         : go(fwd_stream_kernel<KV, NXG, PXL, false, false, T, TF>);
+  return flow != nullptr ? go(fwd_stream_kernel<KV, NXG, PXL, true, false, T, TF>, G::SMEM_BYTES)
+                         : go(fwd_stream_kernel<KV, NXG, PXL, false, false, T, TF>, G::SMEM_BYTES);
 }
 
 // Covered: any output pixel stride >= 81 (a channel slice of the concat buffer, model_pwcnet.py:1424),
@@ -866,8 +884,8 @@ int launch(const T* c1, const T* c2, const TF* flow, float flow_scale, T* out, i
     case 16: PWC_STREAM_GO(4, 4, 6);
     case 32: PWC_STREAM_GO(8, 4, PWC_STREAM_PX32);
     case 64: PWC_STREAM_GO(16, 2, 6);
-    case 96: PWC_STREAM_GO(24, 1, 8);
-    case 128: PWC_STREAM_GO(32, 1, 8);
+    case 96: PWC_STREAM_GO(24, PWC_STREAM_NXG96, 6);
+    case 128: PWC_STREAM_GO(32, PWC_STREAM_NXG128, 6);
     default: return 1;
   }
 #undef PWC_STREAM_GO
