@@ -542,8 +542,26 @@ int pwc_pyramid_fwd_host(pwc_host_ctx* c, const pwc_level_t* lv, int n_levels, i
   // The batch is cut into chunks (batch elements are independent) so that the upload of chunk k+1, the
   // kernels of chunk k and the download of chunk k-1 overlap: PCIe is full duplex and the copies, not the kernels,
   // bound this path (822 MB per step at the headline workload against < 1 ms of kernels).
-  const int nch = B >= 8 ? 8 : (B > 0 ? B : 1);
-  const int cb = (B + nch - 1) / nch;
+  // Chunk sizes ramp up and down (quarter, half, full ... full, half, quarter of B/8): the first upload and the last
+  // download are the only copies that nothing overlaps, so they are kept short.
+  int cstart[40];
+  int nch = 0;
+  {
+    const char* env = getenv("PWC_HOST_CHUNK");  // experiments: images per full chunk
+    const int full = env && atoi(env) > 0 ? atoi(env) : (B >= 8 ? B / 8 : 1);
+    const int ramp[2] = {full >= 4 ? full / 4 : 1, full >= 2 ? full / 2 : 1};
+    int b0 = 0;
+    auto push = [&](int n) {
+      if (n > B - b0) n = B - b0;
+      if (n > 0 && nch < 39) { cstart[nch++] = b0; b0 += n; }
+    };
+    if (B >= 16) { push(ramp[0]); push(ramp[1]); }
+    const int tail = B >= 16 ? ramp[0] + ramp[1] : 0;
+    while (B - b0 > tail && nch < 36) push(full <= B - b0 - tail ? full : B - b0 - tail);
+    if (B >= 16) { push(ramp[1]); push(ramp[0]); }
+    if (b0 < B) push(B - b0);
+    cstart[nch] = B;
+  }
   while ((int)c->ev_in.size() < n_levels * nch) {
     cudaEvent_t e1, e2;
     PWC_CUDA(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
@@ -562,12 +580,23 @@ int pwc_pyramid_fwd_host(pwc_host_ctx* c, const pwc_level_t* lv, int n_levels, i
     if (L.flow && (rc = ctx_reserve(c, 4 * i + 2, npix * 2 * fs))) return rc;
     if ((rc = ctx_reserve(c, 4 * i + 3, npix * ops * es))) return rc;
   }
+  const bool timing = getenv("PWC_HOST_TIMING") != nullptr;
+  const int tmode = timing ? atoi(getenv("PWC_HOST_TIMING")) : 0;  // 2: no downloads, 3: uploads only (results invalid)  // diagnostics: per-stream elapsed times on stderr
+  cudaEvent_t tev[6] = {};
+  if (timing) {
+    for (auto& e : tev) cudaEventCreate(&e);
+    cudaEventRecord(tev[0], c->s_in); cudaEventRecord(tev[1], c->s_run); cudaEventRecord(tev[2], c->s_out);
+  }
   for (int ch = 0; ch < nch; ++ch) {
-    const int b0 = ch * cb, bn = (b0 + cb <= B ? cb : B - b0);
-    if (bn <= 0) break;
+    const int b0 = cstart[ch], bn = cstart[ch + 1] - b0;
+    if (bn <= 0) continue;
     for (int i = 0; i < n_levels; ++i) {
       const pwc_level_t& L = lv[i];
-      const size_t pix0 = (size_t)b0 * L.H * L.W, npix = (size_t)bn * L.H * L.W;
+      // small levels are not worth cutting up (a copy costs ~10 us whatever its size): whole batch with chunk 0
+      const bool whole = (size_t)B * L.H * L.W * L.C * es <= ((size_t)32 << 20);
+      if (whole && ch != 0) continue;
+      const int lb0 = whole ? 0 : b0, lbn = whole ? B : bn;
+      const size_t pix0 = (size_t)lb0 * L.H * L.W, npix = (size_t)lbn * L.H * L.W;
       if (npix == 0) continue;
       const int64_t ops = L.out_pixel_stride ? L.out_pixel_stride : D;
       const size_t o_feat = pix0 * L.C * es, nb_feat = npix * L.C * es;
@@ -584,15 +613,23 @@ int pwc_pyramid_fwd_host(pwc_host_ctx* c, const pwc_level_t* lv, int n_levels, i
         PWC_CUDA(cudaMemcpyAsync(d_fl, (const char*)L.flow + o_flow, nb_flow, cudaMemcpyHostToDevice, c->s_in));
       PWC_CUDA(cudaEventRecord(c->ev_in[e], c->s_in));
       PWC_CUDA(cudaStreamWaitEvent(c->s_run, c->ev_in[e], 0));
-      int rc = fwd_entry(d_c1, d_c2, d_fl, L.flow_scale, d_out, bn, L.H, L.W, L.C, r, dtype, flow_dtype, ops, c->s_run);
+      int rc = tmode >= 3 ? 0 : fwd_entry(d_c1, d_c2, d_fl, L.flow_scale, d_out, lbn, L.H, L.W, L.C, r, dtype, flow_dtype, ops, c->s_run);
       if (rc) return rc;
       PWC_CUDA(cudaEventRecord(c->ev_run[e], c->s_run));
       PWC_CUDA(cudaStreamWaitEvent(c->s_out, c->ev_run[e], 0));
-      PWC_CUDA(cudaMemcpyAsync((char*)L.out + o_out, d_out, nb_out, cudaMemcpyDeviceToHost, c->s_out));
+      if (tmode < 2) PWC_CUDA(cudaMemcpyAsync((char*)L.out + o_out, d_out, nb_out, cudaMemcpyDeviceToHost, c->s_out));
     }
   }
+  if (timing) { cudaEventRecord(tev[3], c->s_in); cudaEventRecord(tev[4], c->s_run); cudaEventRecord(tev[5], c->s_out); }
   PWC_CUDA(cudaStreamSynchronize(c->s_out));
   PWC_CUDA(cudaStreamSynchronize(c->s_in));
+  if (timing) {
+    float a = 0, b = 0, d = 0, e = 0;
+    cudaEventElapsedTime(&a, tev[0], tev[3]); cudaEventElapsedTime(&b, tev[0], tev[4]);
+    cudaEventElapsedTime(&d, tev[0], tev[5]); cudaEventElapsedTime(&e, tev[2], tev[5]);
+    fprintf(stderr, "[pwc host] upload stream done at %.2f ms, kernels at %.2f ms, download at %.2f ms (download stream busy span %.2f ms), %d chunks\n", a, b, d, e, nch);
+    for (auto& ev : tev) cudaEventDestroy(ev);
+  }
   return PWC_OK;
 }
 
