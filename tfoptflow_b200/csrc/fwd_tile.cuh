@@ -13,10 +13,12 @@
 namespace pwc {
 namespace tile {
 
-template <int R_>
+// TW x PX: 32 x 4 (256-pixel tiles, 2 CTAs per SM) for levels with enough tiles to fill the GPU; 16 x 2 (128-pixel tiles,
+// 48 KB, 3 CTAs per SM) for the short pyramid levels, which are latency-bound and want more, lighter CTAs.
+template <int R_, int TW_ = 32, int PX_ = 4>
 struct Cfg {
   static constexpr int R = R_;
-  static constexpr int TH = 8, TW = 32, PX = 4;
+  static constexpr int TH = 8, TW = TW_, PX = PX_;
   static constexpr int ND = 2 * R + 1, D = ND * ND;
   static constexpr int NXG = TW / PX;
   static constexpr int RPAIRS = TH / 2;
@@ -38,15 +40,15 @@ struct Cfg {
   static_assert(NXG * RPAIRS == 32, "one dy per warp");
 };
 
-template <int R, typename T, typename TF>
+template <int R, int TWC, int PXC, typename T, typename TF>
 #ifndef PWC_TILE_MAXNREG
 #define PWC_TILE_MAXNREG 96   /* 2 CTAs/SM (9 warps x 96 regs x 2); measured faster than 112 regs x 1 CTA */
 #endif
-__global__ void __maxnreg__(PWC_TILE_MAXNREG)
+__global__ void __maxnreg__(TWC == 32 ? PWC_TILE_MAXNREG : 72)
 fwd_tile_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* __restrict__ flow,
                 float flow_scale, T* __restrict__ out, int B, int H, int W, int C,
                 int64_t out_pixel_stride, int tiles_x, int tiles_y) {
-  using K = Cfg<R>;
+  using K = Cfg<R, TWC, PXC>;
   constexpr int TH = K::TH, TW = K::TW, PX = K::PX, ND = K::ND, D = K::D, KV = K::KV;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* sA = reinterpret_cast<float4*>(smem_raw);

@@ -28,6 +28,7 @@ std::atomic<int> g_stream_ctas{0};
 std::atomic<int> g_stream_pf{4};
 std::atomic<int> g_stream_dbg{0};
 std::atomic<int> g_overlap{1};
+std::atomic<int> g_tile_small{1};
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -141,29 +142,36 @@ int fwd_typed(const void* c1, const void* c2, const void* flow, float flow_scale
   if (impl == 3) impl = 2;
 #endif
   if (impl == 2) {
-    using K = pwc::tile::Cfg<4>;
-    auto kern = pwc::tile::fwd_tile_kernel<4, T, TF>;
-    static std::atomic<uint64_t> attr_set{0};  // per (T,TF) instantiation; one bit per device
-    int devid = 0;
-    PWC_CUDA(cudaGetDevice(&devid));
-    if (!((attr_set.load() >> devid) & 1)) {
-      PWC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
-      // two co-resident CTAs per SM (93 KB each) hide each other's fill/compute phases
-      PWC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-      if (getenv("PWC_DEBUG_OCC")) {
-        int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, K::NTHREADS, K::SMEM_BYTES);
-        fprintf(stderr, "[pwc] tile kernel occupancy: %d CTAs/SM\n", nb);
+    auto launch_tile = [&](auto cfg, auto kern, int slot) -> int {
+      using K = decltype(cfg);
+      static std::atomic<uint64_t> attr_set[2];  // per (T,TF) instantiation and tile shape; one bit per device
+      int devid = 0;
+      PWC_CUDA(cudaGetDevice(&devid));
+      if (!((attr_set[slot].load() >> devid) & 1)) {
+        PWC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
+        // co-resident CTAs per SM hide each other's fill/compute phases
+        PWC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        if (getenv("PWC_DEBUG_OCC")) {
+          int nb = 0;
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, K::NTHREADS, K::SMEM_BYTES);
+          fprintf(stderr, "[pwc] tile kernel %dx%d occupancy: %d CTAs/SM\n", K::TH, K::TW, nb);
+        }
+        attr_set[slot].fetch_or(uint64_t(1) << devid);
       }
-      attr_set.fetch_or(uint64_t(1) << devid);
-    }
-    const int tiles_x = (W + K::TW - 1) / K::TW, tiles_y = (H + K::TH - 1) / K::TH;
-    const int64_t tiles = (int64_t)tiles_x * tiles_y * B;
-    if (tiles >= (int64_t)1 << 31) return fail(PWC_ERR_BAD_SHAPE, "too many tiles");
-    kern<<<(unsigned)tiles, K::NTHREADS, K::SMEM_BYTES, st>>>((const T*)c1, (const T*)c2, (const TF*)flow, flow_scale,
-                                                             (T*)out, B, H, W, C, ops, tiles_x, tiles_y);
-    PWC_LAUNCH_CHECK();
-    return PWC_OK;
+      const int tiles_x = (W + K::TW - 1) / K::TW, tiles_y = (H + K::TH - 1) / K::TH;
+      const int64_t tiles = (int64_t)tiles_x * tiles_y * B;
+      if (tiles >= (int64_t)1 << 31) return fail(PWC_ERR_BAD_SHAPE, "too many tiles");
+      kern<<<(unsigned)tiles, K::NTHREADS, K::SMEM_BYTES, st>>>((const T*)c1, (const T*)c2, (const TF*)flow, flow_scale,
+                                                               (T*)out, B, H, W, C, ops, tiles_x, tiles_y);
+      PWC_LAUNCH_CHECK();
+      return PWC_OK;
+    };
+    // short levels: fewer full-size tiles than SMs -> the small tile shape (more, lighter CTAs; measured: level 5
+    // 76 -> 46 us, while level 4 with 256 full-size tiles is faster as it is: 91 vs 119 us)
+    const int64_t big_tiles = (int64_t)((W + 31) / 32) * ((H + 7) / 8) * B;
+    if (big_tiles < (int64_t)dev.sms && g_tile_small.load())
+      return launch_tile(pwc::tile::Cfg<4, 16, 2>(), pwc::tile::fwd_tile_kernel<4, 16, 2, T, TF>, 1);
+    return launch_tile(pwc::tile::Cfg<4, 32, 4>(), pwc::tile::fwd_tile_kernel<4, 32, 4, T, TF>, 0);
   }
   const int64_t total = (int64_t)B * H * W * D;
   pwc::fwd_generic_kernel<T, TF><<<grid_for(total, 256, dev.sms), 256, 0, st>>>(
@@ -375,6 +383,10 @@ int pwc_set_option(const char* key, int value) {
   }
   if (!strcmp(key, "overlap_levels")) {
     g_overlap.store(value);
+    return PWC_OK;
+  }
+  if (!strcmp(key, "tile_small")) {  // 0: always the 8x32 tile shape
+    g_tile_small.store(value);
     return PWC_OK;
   }
   if (!strcmp(key, "stream_debug")) {  // timing experiments only; results are wrong when non-zero
