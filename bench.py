@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--search-range", type=int, default=4)
     ap.add_argument("--flow", default="smooth", choices=["smooth", "stress", "zero"])
     ap.add_argument("--fwd-impl", type=int, default=0, help="library option fwd_impl (0 = auto)")
+    ap.add_argument("--opt", action="append", default=[], help="library option key=value (experiments)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 20)")
@@ -203,6 +204,9 @@ def run_ours(a):
     lib = _ffi.load()
     if a.fwd_impl:
         _ffi.set_option("fwd_impl", a.fwd_impl)
+    for kv in a.opt:
+        k, v = kv.split("=")
+        _ffi.set_option(k, int(v))
 
     ndt = np_dtype(a.dtype)
     elt = 4 if a.dtype == "fp32" else 2

@@ -12,7 +12,8 @@ for kv in sys.argv[2:]:
     else: _ffi.set_option(k, int(v))
 _ffi.set_option("fwd_impl", 3)
 dev = torch.device("cuda", 0)
-d = synth.make_level(B, 112, 256, 32, 1971, np.float32, "smooth")
+H, W, C = [int(x) for x in os.environ.get("SHAPE", "112,256,32").split(",")]
+d = synth.make_level(B, H, W, C, 1971, np.float32, "smooth")
 L = {k: (None if d[k] is None else torch.from_numpy(d[k]).to(dev)) for k in ("c1", "c2", "flow")}
 L["scaler"] = 5.0
 plan = pyramid.PyramidPlan([L], 4)
@@ -32,7 +33,7 @@ for w in range(NW):
         ev.append((x >> 16, w, (x >> 12) & 0xf, x & 0xfff))
 ev.sort()
 t0 = ev[0][0]
-names = {1: "P slab start", 2: "P A issued", 3: "P coords done", 4: "P emptyB ok", 5: "P slab full", 8: "C grab", 9: "C waits ok", 10: "C corr done", 11: "C epi done"}
+names = {1: "P slab start", 2: "P A issued", 3: "P coords done", 4: "P emptyB ok", 5: "P slab full", 8: "C grab", 9: "C waits ok", 10: "C corr done", 11: "C epi done", 12: "S store start", 13: "C refill done", 14: "C pre-fence", 15: "C post-fence"}
 lo, hi = int(os.environ.get("T0", 60000)), int(os.environ.get("T1", 75000))
 print(f"events={len(ev)} span={ev[-1][0]-t0} cycles")
 for t, w, c, v in ev:
@@ -50,3 +51,13 @@ for t, w, c, v in ev:
 for k in sorted(dur):
     x = np.array(dur[k])
     print(f"{names.get(k[0], k[0]):14s} -> {names.get(k[1], k[1]):14s}: n={len(x):4d} mean={x.mean():8.0f} med={np.median(x):8.0f} max={x.max():8d}")
+# per-task phase durations of one warp (WARP env), to spot which tasks are slow
+if os.environ.get("WARP"):
+    w0 = int(os.environ["WARP"])
+    seq = [(t - t0, c, v) for t, w, c, v in ev if w == w0]
+    cur = {}
+    for t, c, v in seq:
+        if c == 8: cur = {"t": v, 8: t}
+        elif c in (9, 10, 11) and cur: cur[c] = t
+        if c == 11 and all(k in cur for k in (8, 9, 10, 11)):
+            print(f"task {cur['t']:4d}: wait {cur[9]-cur[8]:6d} corr {cur[10]-cur[9]:6d} epi {cur[11]-cur[10]:6d}")

@@ -729,16 +729,23 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
     if (slab_ok && arrive_b) mbar_arrive(&emptyB[jg % NBB]);
     if (pair_ok && arrive_a) {
       if constexpr (ATMA) {
-        __threadfence_block();
+        // no fence: every shared-memory read of this slot has already delivered its value (the FFMA2s consumed it, and
+        // __syncwarp above covers the other lanes); a MEMBAR here would also wait for the previous task's global stores
         if (atomicAdd(&a_cnt[sa], 1) == 5) {  // last of the 6 arrivals: the slot is free, refill it with pair ag + NAP
           a_cnt[sa] = 0;
           if (ag + G::NAP < s_misc[3]) refill_pair_tma<G, T>(c1, P, segs, nseg, ag + G::NAP, sA, fullA);
+          if ((P.dbg & 16) && blockIdx.x == 0 && lane == 0 && tr_n < TRACE_LEN) g_trace[warp][tr_n++] = ((unsigned long long)clock64() << 16) | (13 << 12) | (lane & 0xfff);
         }
       } else {
         mbar_arrive(&emptyA[ag % NBA]);
       }
     }
 
+    // tasks that only exist to keep the ring arithmetic regular (warm-up slabs above / below the image) write nothing
+    if (!__any_sync(0xffffffffu, store)) {
+      PWC_TR(11, t);
+      continue;
+    }
     // epilogue: lane L owns, for each pixel p, the 9 channels [dyi*9, dyi*9+9) of pixel (ya, xb+p).
     // Runs go through a per-warp transposition buffer so that each store instruction writes whole runs.
     const int xb = sg.x0 + xg * G::PX;

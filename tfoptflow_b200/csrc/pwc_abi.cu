@@ -29,6 +29,7 @@ std::atomic<int> g_stream_pf{4};
 std::atomic<int> g_stream_dbg{0};
 std::atomic<int> g_overlap{1};
 std::atomic<int> g_tile_small{1};
+std::atomic<int> g_side_reverse{1};
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -385,6 +386,10 @@ int pwc_set_option(const char* key, int value) {
     g_overlap.store(value);
     return PWC_OK;
   }
+  if (!strcmp(key, "side_reverse")) {  // order in which the short levels are launched on the side streams
+    g_side_reverse.store(value);
+    return PWC_OK;
+  }
   if (!strcmp(key, "tile_small")) {  // 0: always the 8x32 tile shape
     g_tile_small.store(value);
     return PWC_OK;
@@ -478,7 +483,9 @@ int pwc_pyramid_fwd(const pwc_level_t* levels, int n_levels, int B, int r, int d
   // ... then the short levels side by side (few CTAs each; same H threshold as the kernel choice)
   if (S) {
     PWC_CUDA(cudaEventRecord(S->fork, main_st));
-    for (int i = 0; i < n_levels; ++i) {
+    // largest first: its CTAs take whole SMs (2 x 93 KB); the lighter kernels then fill what is left
+    for (int ii = 0; ii < n_levels; ++ii) {
+      const int i = g_side_reverse.load() ? n_levels - 1 - ii : ii;
       const pwc_level_t& L = levels[i];
       if (L.H >= 40) continue;
       const int k = n_side++ % 3;
