@@ -44,10 +44,10 @@ constexpr size_t SMEM_LIMIT = 232448;
 #define PWC_STREAM_LD4 ld4
 #endif
 #ifndef PWC_STREAM_NSLAB8
-#define PWC_STREAM_NSLAB8 8
+#define PWC_STREAM_NSLAB8 12
 #endif
 #ifndef PWC_STREAM_NAP8
-#define PWC_STREAM_NAP8 12
+#define PWC_STREAM_NAP8 14
 #endif
 #ifndef PWC_STREAM_GD
 #define PWC_STREAM_GD 3
@@ -60,6 +60,15 @@ constexpr size_t SMEM_LIMIT = 232448;
 #endif
 #ifndef PWC_STREAM_NSW
 #define PWC_STREAM_NSW 0
+#endif
+#ifndef PWC_STREAM_NSLAB16
+#define PWC_STREAM_NSLAB16 10
+#endif
+#ifndef PWC_STREAM_NAP16
+#define PWC_STREAM_NAP16 14
+#endif
+#ifndef PWC_STREAM_FULLSTAGE
+#define PWC_STREAM_FULLSTAGE 0   /* whole-task staging costs 41 KB that buys more as 4 extra slab slots: 243 -> 225 us */
 #endif
 #ifndef PWC_STREAM_PX32
 #define PWC_STREAM_PX32 6
@@ -114,11 +123,11 @@ struct Geo {
   static constexpr int EMPTYB_COUNT = (NXG == 4 ? 2 : 1) + 1;
   static constexpr int LPP = KV >= 8 ? 8 : KV;        // producer lanes per pixel
   static constexpr int KQ = KV / LPP;                 // kv chunks per lane
-  static constexpr int NSLAB = PX <= 4 ? 10 : (KV == 32 && NXG == 2) ? 4 : (KV == 24 && NXG == 2) ? 6 : KV == 32 ? 6 : (KV == 16 ? (PX <= 6 ? 8 : 6) : (KV == 8 ? PWC_STREAM_NSLAB8 : 7));
-  static constexpr int NAP = PX <= 4 ? 14 : (KV == 32 && NXG == 2) ? 8 : (KV == 24 && NXG == 2) ? 10 : KV == 32 ? 12 : (KV == 8 ? PWC_STREAM_NAP8 : 12);     // even: the wrap-around keeps consecutive pairs 2 bank groups apart
+  static constexpr int NSLAB = PX <= 4 ? 10 : (KV == 32 && NXG == 2) ? 4 : (KV == 24 && NXG == 2) ? 6 : KV == 32 ? 6 : (KV == 16 ? (PX <= 6 ? PWC_STREAM_NSLAB16 : 6) : (KV == 8 ? PWC_STREAM_NSLAB8 : 7));
+  static constexpr int NAP = PX <= 4 ? 14 : (KV == 32 && NXG == 2) ? 8 : (KV == 24 && NXG == 2) ? 10 : KV == 32 ? 12 : (KV == 8 ? PWC_STREAM_NAP8 : (KV == 16 && PX <= 6 ? PWC_STREAM_NAP16 : 12));     // even: the wrap-around keeps consecutive pairs 2 bank groups apart
   // transposition buffer per compute warp: all PX pixels at once where shared memory allows (one warp sync per task),
   // else two pixels, double buffered
-  static constexpr bool FULLSTAGE = PX <= 6 && KV <= 16;
+  static constexpr bool FULLSTAGE = PWC_STREAM_FULLSTAGE && PX <= 6 && KV <= 16;
   static constexpr int STAGE_WORDS = FULLSTAGE ? 320 * PX : 640;
   static constexpr size_t OFF_B = 0;
   static constexpr size_t OFF_A = OFF_B + (size_t)NSLAB * BSLOT * 16;
