@@ -27,6 +27,9 @@ std::atomic<int> g_fwd_impl{0};
 std::atomic<int> g_stream_ctas{0};
 std::atomic<int> g_stream_pf{4};
 std::atomic<int> g_stream_dbg{0};
+// levels at least this tall take the streaming kernel (it pays ~5 warm-up slabs per strip segment): measured
+// 28 rows 84 us streaming vs 91 us tiled, 14 rows 56 vs 46 us
+constexpr int kTallMinH = 28;
 std::atomic<int> g_overlap{1};
 std::atomic<int> g_tile_small{1};
 std::atomic<int> g_side_reverse{1};
@@ -116,7 +119,7 @@ int fwd_typed(const void* c1, const void* c2, const void* flow, float flow_scale
   const bool tuned_ok = r == 4 && vec_ok;
   // auto: the streaming kernel wins on tall levels (it pays ~5 warm-up slabs per strip segment), the tiled kernel
   // on short ones; measured crossover between H = 28 and H = 56 (profiles/r01_notes.md)
-  if (impl == 0) impl = !tuned_ok ? 1 : (H >= 40 ? 3 : 2);
+  if (impl == 0) impl = !tuned_ok ? 1 : (H >= kTallMinH ? 3 : 2);
   // un-warped small level (the pyramid top): too few tiles for the tiled kernel, one thread per output element wins
   if (g_fwd_impl.load() == 0 && flow == nullptr && vec_ok && (int64_t)B * H * W <= 16384) {
     const int64_t total = (int64_t)B * H * W * D;
@@ -475,7 +478,7 @@ int pwc_pyramid_fwd(const pwc_level_t* levels, int n_levels, int B, int r, int d
   // tall levels first, in order, on the caller's stream (their persistent kernels want every SM) ...
   for (int i = 0; i < n_levels; ++i) {
     const pwc_level_t& L = levels[i];
-    if (S && L.H < 40) continue;
+    if (S && L.H < kTallMinH) continue;
     int rc = fwd_entry(L.c1, L.c2, L.flow, L.flow_scale, L.out, B, L.H, L.W, L.C, r, dtype, flow_dtype,
                        L.out_pixel_stride, main_st);
     if (rc) return rc;
@@ -487,7 +490,7 @@ int pwc_pyramid_fwd(const pwc_level_t* levels, int n_levels, int B, int r, int d
     for (int ii = 0; ii < n_levels; ++ii) {
       const int i = g_side_reverse.load() ? n_levels - 1 - ii : ii;
       const pwc_level_t& L = levels[i];
-      if (L.H >= 40) continue;
+      if (L.H >= kTallMinH) continue;
       const int k = n_side++ % 3;
       if (!used[k]) { PWC_CUDA(cudaStreamWaitEvent(S->s[k], S->fork, 0)); used[k] = true; }
       int rc = fwd_entry(L.c1, L.c2, L.flow, L.flow_scale, L.out, B, L.H, L.W, L.C, r, dtype, flow_dtype,
