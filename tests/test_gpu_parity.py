@@ -226,6 +226,26 @@ def test_out_slice_of_concat_buffer(dev):
             assert torch.all(buf[..., 81:] == -7.0)
 
 
+def test_half_inputs_on_8_byte_boundary(dev):
+    # a 16-bit view that starts 8 bytes into its allocation is fine for the vector loads but not for TMA (16-byte
+    # global addresses): the streaming kernel must take its LDG path for c1 and still agree with the oracle
+    d = synth.make_level(1, 44, 40, 32, 700, np.float16, "smooth")
+    ref = O.warp_cost_volume(d["c1"], d["c2"], d["flow"], 4).astype(np.float32)
+
+    def shifted(a):
+        flat = torch.empty(a.size + 4, dtype=torch.float16, device=dev)
+        v = flat[4:].view(*a.shape)
+        v.copy_(torch.from_numpy(a))
+        assert v.data_ptr() % 16 == 8
+        return v
+
+    c1, c2, flow = shifted(d["c1"]), shifted(d["c2"]), to_dev(d["flow"], dev)
+    for impl in IMPLS:
+        _ffi.set_option("fwd_impl", impl)
+        got = warp_cost_volume(c1, c2, flow, 4).float().cpu().numpy()
+        assert_close(got, ref, 1e-2, f"shifted fp16 impl {impl}")
+
+
 def test_non_contiguous_and_dlpack_inputs(dev):
     d = synth.make_level(1, 12, 16, 16, 500, np.float32, "smooth")
     c1 = to_dev(d["c1"], dev).permute(0, 3, 1, 2).contiguous().permute(0, 2, 3, 1)  # NHWC view of NCHW storage

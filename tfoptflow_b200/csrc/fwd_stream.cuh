@@ -877,9 +877,9 @@ int launch_cfg(const T* c1, const T* c2, const TF* flow, float flow_scale, T* ou
     kern<<<(unsigned)grid, G::NTHREADS, smem_bytes, st>>>(c1, c2, flow, out, P);
     return 0;
   };
-  // TMA needs 16-byte aligned global rows: C % 8 == 0 for 16-bit elements, C % 4 == 0 for fp32, and an aligned base
-  // (checked by the caller); stream_debug bit 8 forces the LDG/STS c1 path
-  if (!(dbg & 8) && (C * (int)sizeof(T)) % 16 == 0) {
+  // TMA needs 16-byte aligned global rows: C % 8 == 0 for 16-bit elements, C % 4 == 0 for fp32, and a 16-byte aligned
+  // base (a 16-bit view may start on an 8-byte boundary: LDG path then); stream_debug bit 8 forces the LDG/STS c1 path
+  if (!(dbg & 8) && (C * (int)sizeof(T)) % 16 == 0 && reinterpret_cast<uintptr_t>(c1) % 16 == 0) {
     using GT = Geo<KV, NXG, PXL, (int)sizeof(T) * 4>;
     return flow != nullptr ? go(fwd_stream_kernel<KV, NXG, PXL, true, true, T, TF>, GT::SMEM_BYTES)
                            : go(fwd_stream_kernel<KV, NXG, PXL, false, true, T, TF>, GT::SMEM_BYTES);
