@@ -79,6 +79,70 @@ bwd_corr_kernel(const T* __restrict__ g, const T* __restrict__ out, const T* __r
   }
 }
 
+
+// Register-tiled variant for r = 4 (the model's search range): one thread owns PXT = 4 pixels along x and CVT = 2
+// channel quads.  Every neighbour vector is loaded once per thread and used for up to 4 (pixel, dx) combinations, and
+// every g' value serves 8 channels: ~2.6x less L1 traffic per FMA than the one-pixel kernel, which is bound by L1
+// bandwidth (81 LDG.128 per output float4).  Needs W % 4 == 0 and C % 8 == 0.
+//   MODE 0: dc1[p,c]   += g'[p, (dy,dx)] * warp[p + (dy,dx), c]
+//   MODE 1: dwarp[q,c] += g'[s, (dy,dx)] * c1[s, c],  s = q - (dy,dx)
+template <int MODE, typename T, typename TO>
+__global__ void __launch_bounds__(256)
+bwd_corr_r4_tiled_kernel(const T* __restrict__ g, const T* __restrict__ out, const T* __restrict__ other,
+                         TO* __restrict__ dst, int B, int H, int W, int C, int64_t gps, int64_t ops) {
+  constexpr int R = 4, N = 9, PXT = 4, CVT = 2;
+  const int CG = C / (4 * CVT), WG = W / PXT;
+  const int64_t total = (int64_t)B * H * WG * CG;
+  const float inv_c = 1.0f / (float)C;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % CG) * 4 * CVT;
+    const int64_t pg = idx / CG;
+    const int x0 = (int)(pg % WG) * PXT, y = (int)((pg / WG) % H), b = (int)(pg / ((int64_t)WG * H));
+    float acc[PXT][4 * CVT];
+#pragma unroll
+    for (int i = 0; i < PXT; ++i)
+#pragma unroll
+      for (int k = 0; k < 4 * CVT; ++k) acc[i][k] = 0.0f;
+    const size_t row0 = ((size_t)b * H + y) * W;
+#pragma unroll 1
+    for (int dyi = 0; dyi < N; ++dyi) {
+      const int yy = MODE == 0 ? y + dyi - R : y - (dyi - R);  // row of the neighbour vector
+      if (yy < 0 || yy >= H) continue;
+      const size_t rown = ((size_t)b * H + yy) * W;
+#pragma unroll
+      for (int k = 0; k < PXT + 2 * R; ++k) {  // neighbour column xx = x0 - R + k
+        const int xx = x0 - R + k;
+        if (xx < 0 || xx >= W) continue;
+        float o[4 * CVT];
+#pragma unroll
+        for (int v = 0; v < CVT; ++v) {
+          const float4 f = ld4(other + (rown + xx) * C + c + 4 * v);
+          o[4 * v] = f.x; o[4 * v + 1] = f.y; o[4 * v + 2] = f.z; o[4 * v + 3] = f.w;
+        }
+#pragma unroll
+        for (int i = 0; i < PXT; ++i) {
+          // MODE 0: xx = x0 + i + (dxi - R)  ->  dxi = k - i ;  MODE 1: xx = x0 + i - (dxi - R)  ->  dxi = 2R + i - k
+          const int dxi = MODE == 0 ? k - i : 2 * R + i - k;
+          if (dxi < 0 || dxi >= N) continue;
+          const float gp = gprime<T>(g, out, MODE == 0 ? row0 + x0 + i : rown + xx, dyi * N + dxi, gps, ops);
+#pragma unroll
+          for (int q = 0; q < 4 * CVT; ++q) acc[i][q] = fmaf(gp, o[q], acc[i][q]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < PXT; ++i)
+#pragma unroll
+      for (int v = 0; v < CVT; ++v) {
+        Vec<4> r4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) r4.v[q] = acc[i][4 * v + q] * inv_c;
+        stv<4, TO>(dst + (row0 + x0 + i) * C + c + 4 * v, r4);
+      }
+  }
+}
+
 // dense_image_warp backward: one warp per output pixel, lanes stride over channels.
 // dimg_acc is an fp32 accumulator (zero-initialised by the caller); dflow gets -(dalpha)*mask*scale.
 template <int VEC, typename T, typename TF, typename TG>

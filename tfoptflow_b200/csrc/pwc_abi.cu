@@ -31,6 +31,7 @@ std::atomic<int> g_stream_dbg{0};
 // 28 rows 84 us streaming vs 91 us tiled, 14 rows 56 vs 46 us
 constexpr int kTallMinH = 28;
 std::atomic<int> g_overlap{1};
+std::atomic<int> g_bwd_tiled{1};
 std::atomic<int> g_tile_small{1};
 std::atomic<int> g_side_reverse{1};
 
@@ -255,7 +256,11 @@ template <int MODE, typename T, typename TO>
 int bwd_corr_launch(const void* g, const void* out, const void* other, void* dst, int B, int H, int W, int C, int r,
                     int64_t gps, int64_t ops, cudaStream_t st, const DevInfo& dev) {
   const size_t va = sizeof(T) * 4;
-  if (C % 4 == 0 && aligned(other, va) && aligned(dst, sizeof(TO) * 4)) {
+  if (r == 4 && C % 8 == 0 && W % 4 == 0 && aligned(other, va) && aligned(dst, sizeof(TO) * 4) && g_bwd_tiled.load()) {
+    const int64_t total = (int64_t)B * H * (W / 4) * (C / 8);
+    pwc::bwd_corr_r4_tiled_kernel<MODE, T, TO><<<grid_for(total, 256, dev.sms), 256, 0, st>>>(
+        (const T*)g, (const T*)out, (const T*)other, (TO*)dst, B, H, W, C, gps, ops);
+  } else if (C % 4 == 0 && aligned(other, va) && aligned(dst, sizeof(TO) * 4)) {
     const int64_t total = (int64_t)B * H * W * (C / 4);
     pwc::bwd_corr_kernel<MODE, 4, T, TO><<<grid_for(total, 256, dev.sms), 256, 0, st>>>(
         (const T*)g, (const T*)out, (const T*)other, (TO*)dst, B, H, W, C, r, gps, ops);
@@ -387,6 +392,10 @@ int pwc_set_option(const char* key, int value) {
   }
   if (!strcmp(key, "overlap_levels")) {
     g_overlap.store(value);
+    return PWC_OK;
+  }
+  if (!strcmp(key, "bwd_tiled")) {  // 0: one-pixel-per-thread backward correlation kernels
+    g_bwd_tiled.store(value);
     return PWC_OK;
   }
   if (!strcmp(key, "side_reverse")) {  // order in which the short levels are launched on the side streams
