@@ -145,22 +145,28 @@ bwd_corr_r4_tiled_kernel(const T* __restrict__ g, const T* __restrict__ out, con
 
 // dense_image_warp backward: one warp per output pixel, lanes stride over channels.
 // dimg_acc is an fp32 accumulator (zero-initialised by the caller); dflow gets -(dalpha)*mask*scale.
-template <int VEC, typename T, typename TF, typename TG>
+// LPP = lanes per pixel (8 / 16 / 32): with 32 or 64 channels a whole warp per pixel would leave 3/4 or 1/2 of the
+// lanes idle, so a warp takes 32 / LPP pixels.
+template <int VEC, int LPP, typename T, typename TF, typename TG>
 __global__ void __launch_bounds__(256)
 warp_bwd_kernel(const TG* __restrict__ gout, const T* __restrict__ img, const TF* __restrict__ flow,
                 float flow_scale, float* __restrict__ dimg_acc, TF* __restrict__ dflow,
                 int B, int H, int W, int C) {
-  const int lane = threadIdx.x & 31;
+  constexpr int PPW = 32 / LPP;  // pixels per warp
+  const int lane = threadIdx.x & (LPP - 1), sub = (threadIdx.x & 31) / LPP;
   const int64_t npix = (int64_t)B * H * W;
   const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < npix; p += warps_total) {
+  // the trip count is warp-uniform (shuffles below): pixels beyond the end are clamped and not written
+  for (int64_t p0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * PPW; p0 < npix; p0 += warps_total * PPW) {
+    const bool valid = p0 + sub < npix;
+    const int64_t p = valid ? p0 + sub : npix - 1;
     const int x = (int)(p % W), y = (int)((p / W) % H), b = (int)(p / ((int64_t)W * H));
     const SampleCoord s = sample_coord<T, TF>(flow, flow_scale, b, y, x, H, W);
     const float ax = s.ax, ay = s.ay;
     const float w_tl = (1.f - ay) * (1.f - ax), w_tr = (1.f - ay) * ax, w_bl = ay * (1.f - ax), w_br = ay * ax;
     float dax = 0.f, day = 0.f;
     const size_t i_tl = (size_t)s.pix * C, i_tr = i_tl + C, i_bl = i_tl + (size_t)W * C, i_br = i_bl + C;
-    for (int c = lane * VEC; c < C; c += 32 * VEC) {
+    for (int c = lane * VEC; valid && c < C; c += LPP * VEC) {
       const Vec<VEC> gw = ldv<VEC, TG>(gout + (size_t)p * C + c);
       const Vec<VEC> tl = ldv<VEC, T>(img + i_tl + c), tr = ldv<VEC, T>(img + i_tr + c);
       const Vec<VEC> bl = ldv<VEC, T>(img + i_bl + c), br = ldv<VEC, T>(img + i_br + c);
@@ -191,11 +197,11 @@ warp_bwd_kernel(const TG* __restrict__ gout, const T* __restrict__ img, const TF
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = LPP / 2; o > 0; o >>= 1) {
       dax += __shfl_xor_sync(0xffffffffu, dax, o);
       day += __shfl_xor_sync(0xffffffffu, day, o);
     }
-    if (lane == 0) {
+    if (lane == 0 && valid) {
       dflow[2 * p] = ElemTraits<TF>::from_f(-day * s.my * flow_scale);
       dflow[2 * p + 1] = ElemTraits<TF>::from_f(-dax * s.mx * flow_scale);
     }

@@ -277,13 +277,19 @@ template <typename T, typename TF, typename TG>
 int warp_bwd_launch(const void* gout, const void* img, const void* flow, float scale, float* dimg_acc, void* dflow,
                     int B, int H, int W, int C, cudaStream_t st, const DevInfo& dev) {
   const int64_t npix = (int64_t)B * H * W;
-  const int grid = grid_for(npix * 32, 256, dev.sms);
   if (C % 4 == 0 && aligned(gout, sizeof(TG) * 4) && aligned(img, sizeof(T) * 4) && aligned(dimg_acc, 16)) {
-    pwc::warp_bwd_kernel<4, T, TF, TG><<<grid, 256, 0, st>>>((const TG*)gout, (const T*)img, (const TF*)flow, scale,
-                                                            dimg_acc, (TF*)dflow, B, H, W, C);
+    const int lpp = C <= 32 ? 8 : (C <= 64 ? 16 : 32);  // lanes per pixel, 4 channels per lane and step
+    const int grid = grid_for(npix * lpp, 256, dev.sms);
+    auto go = [&](auto kern) {
+      kern<<<grid, 256, 0, st>>>((const TG*)gout, (const T*)img, (const TF*)flow, scale, dimg_acc, (TF*)dflow, B, H, W, C);
+    };
+    if (lpp == 8) go(pwc::warp_bwd_kernel<4, 8, T, TF, TG>);
+    else if (lpp == 16) go(pwc::warp_bwd_kernel<4, 16, T, TF, TG>);
+    else go(pwc::warp_bwd_kernel<4, 32, T, TF, TG>);
   } else {
-    pwc::warp_bwd_kernel<1, T, TF, TG><<<grid, 256, 0, st>>>((const TG*)gout, (const T*)img, (const TF*)flow, scale,
-                                                            dimg_acc, (TF*)dflow, B, H, W, C);
+    const int grid = grid_for(npix * 32, 256, dev.sms);
+    pwc::warp_bwd_kernel<1, 32, T, TF, TG><<<grid, 256, 0, st>>>((const TG*)gout, (const T*)img, (const TF*)flow, scale,
+                                                                dimg_acc, (TF*)dflow, B, H, W, C);
   }
   PWC_LAUNCH_CHECK();
   return PWC_OK;
