@@ -7,6 +7,9 @@
 //   dflow      = -(d/dalpha . dwarp) * clamp-mask * flow_scale
 #pragma once
 #include "common.cuh"
+#ifndef PWC_BWD_MINBLOCKS
+#define PWC_BWD_MINBLOCKS 3   /* 3 blocks of 256 per SM (<= 85 registers): level-2 fwd+bwd 2.16 -> 1.72 ms; 4 blocks: 1.93 ms */
+#endif
 
 namespace pwc {
 
@@ -87,7 +90,7 @@ bwd_corr_kernel(const T* __restrict__ g, const T* __restrict__ out, const T* __r
 //   MODE 0: dc1[p,c]   += g'[p, (dy,dx)] * warp[p + (dy,dx), c]
 //   MODE 1: dwarp[q,c] += g'[s, (dy,dx)] * c1[s, c],  s = q - (dy,dx)
 template <int MODE, typename T, typename TO>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, PWC_BWD_MINBLOCKS)
 bwd_corr_r4_tiled_kernel(const T* __restrict__ g, const T* __restrict__ out, const T* __restrict__ other,
                          TO* __restrict__ dst, int B, int H, int W, int C, int64_t gps, int64_t ops) {
   constexpr int R = 4, N = 9, PXT = 4, CVT = 2;
