@@ -123,6 +123,13 @@ int fwd_typed(const void* c1, const void* c2, const void* flow, float flow_scale
   if (impl == 0) impl = !tuned_ok ? 1 : (H >= kTallMinH ? 3 : 2);
   // un-warped small level (the pyramid top): too few tiles for the tiled kernel, one thread per output element wins
   if (g_fwd_impl.load() == 0 && flow == nullptr && vec_ok && (int64_t)B * H * W <= 16384) {
+    if (r == 4 && W % 2 == 0) {
+      const int64_t total = (int64_t)B * H * (W / 2) * 27;
+      pwc::fwd_noflow_r4_tiled_kernel<T><<<grid_for(total, 256, dev.sms), 256, 0, st>>>((const T*)c1, (const T*)c2, (T*)out,
+                                                                                      B, H, W, C, ops);
+      PWC_LAUNCH_CHECK();
+      return PWC_OK;
+    }
     const int64_t total = (int64_t)B * H * W * D;
     pwc::fwd_noflow_vec4_kernel<T><<<grid_for(total, 256, dev.sms), 256, 0, st>>>((const T*)c1, (const T*)c2, (T*)out, B, H,
                                                                                 W, C, r, ops);
