@@ -56,7 +56,7 @@ constexpr size_t SMEM_LIMIT = 232448;
 #define PWC_STREAM_NXG96 2
 #endif
 #ifndef PWC_STREAM_NXG128
-#define PWC_STREAM_NXG128 2
+#define PWC_STREAM_NXG128 1
 #endif
 #ifndef PWC_STREAM_NSW
 #define PWC_STREAM_NSW 0
@@ -142,6 +142,10 @@ struct Geo {
   static constexpr size_t SMEM_BYTES = OFF_SBAR + 2 * NCWG * 8;
   static_assert(SMEM_BYTES <= SMEM_LIMIT, "shared memory budget");
   static_assert(KV % LPP == 0 && KV % KP == 0 && NAP % 2 == 0, "channel split / ring");
+  // An edge task waits for the 4 slabs of its group and for the c1 pairs l-5 .. l+3 of those slabs at once: 9 pairs
+  // and 4 slabs must be resident together or the task can never start (found by scripts/stress_stream.py: 8 pair
+  // slots deadlock).  One spare of each keeps the producers from stalling on the group boundary.
+  static_assert(NAP >= 10 && NSLAB >= 5, "ring too short for an edge task");
 };
 
 struct Seg {
