@@ -4,6 +4,9 @@ import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tfoptflow_b200 import synth, warp_cost_volume
 B, H, W, C = [int(x) for x in sys.argv[1:5]]
+from tfoptflow_b200 import _ffi
+for kv in sys.argv[5:]:
+    k, v = kv.split('='); _ffi.set_option(k, int(v))
 dev = torch.device("cuda", 0)
 d = synth.make_level(B, H, W, C, 1971, np.float32, "smooth", with_grad=True)
 c1, c2, flow = (torch.from_numpy(d[k]).to(dev).requires_grad_() for k in ("c1", "c2", "flow"))
