@@ -11,13 +11,16 @@ plus the analytic backward that TensorFlow 1.10 autodiff would generate for
 them (the reference has no backward code of its own, it
 is selected by `optim.minimize`, tfoptflow/model_pwcnet.py:547-550).
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for
-this path, and its arithmetic lives in third-party TensorFlow 1.10.1
-(tfoptflow/setup/dlubu36.yml:153) which cannot be imported or installed in this
-image (Python 3.12, no network).  The oracle is therefore pinned only by the
-known-answer vectors of SURVEY.md section 8c (tests/test_oracle.py), by an
-independent second formulation (torch grid_sample / unfold) and by fp64 finite
-differences - not by outputs of the reference itself.
+PARITY PINNED TO THE REFERENCE'S OWN SOURCE: TensorFlow 1.10.1 (tfoptflow/setup/dlubu36.yml:153) cannot be
+imported or installed in this image (Python 3.12, no network) and the reference ships no tests for this path, but
+its two hot-path files are plain Python over ~25 TF symbols.  tests/golden/tf_numpy_shim.py supplies those symbols
+on numpy, imports tfoptflow/core_warp.py and core_costvol.py UNMODIFIED and executes them;
+tests/test_oracle_vs_reference.py asserts np.array_equal(oracle, reference) on the level shapes of every
+BASELINE.json config (fp32 + fp16, r = 4 and 8) and checks the backward below against float64 torch.autograd
+through the same unmodified source; tests/golden/*.npz are generated from that import
+(tests/golden/make_golden_from_reference.py).  What stays an assumption is kernel-level TF behaviour the Python
+source does not show: fp16 reduce_mean accumulating in fp32, and the gradient routing of Maximum/Minimum at exact
+ties (TF 1.x `_MaximumMinimumGrad`), which only matters at integer coordinates / zero pre-activations.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference arm
 may import this module.  The product path (tfoptflow_b200/) never does.

@@ -1,6 +1,6 @@
-"""Pins oracle/pwc_oracle.py with the known-answer vectors of SURVEY.md section 8c and
-the committed golden fixtures.  CPU only.  (The reference ships no tests for this
-path and TensorFlow 1.10 cannot run here, so these vectors ARE the pin.)"""
+"""Known-answer vectors of SURVEY.md section 8c for oracle/pwc_oracle.py, and the committed golden fixtures
+(tests/golden/*.npz, generated from the reference's own source by tests/golden/make_golden_from_reference.py).
+CPU only.  The bit-for-bit pin against the imported reference is tests/test_oracle_vs_reference.py."""
 import glob
 import os
 
@@ -188,11 +188,10 @@ def test_golden_fixtures(path):
     assert out.dtype == z["out"].dtype
     assert np.array_equal(out, z["out"])
     if "dc1" in z.files:
+        # fixtures hold float64 autograd through the reference source (or the oracle itself for the tie case)
         dc1, dc2, dflow = O.warp_cost_volume_bwd(z["g"], z["c1"], z["c2"], flow, r, fs)
-        np.testing.assert_allclose(dc1, z["dc1"], rtol=1e-6, atol=1e-7)
-        np.testing.assert_allclose(dc2, z["dc2"], rtol=1e-6, atol=1e-7)
-        if dflow is not None:
-            np.testing.assert_allclose(dflow, z["dflow"], rtol=1e-6, atol=1e-6)
+        for got, want in ((dc1, z["dc1"]), (dc2, z["dc2"])) + (((dflow, z["dflow"]),) if dflow is not None else ()):
+            assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
 
 
 def test_synth_byte_counts_match_survey():
