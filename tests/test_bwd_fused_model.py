@@ -1,0 +1,116 @@
+"""CPU model of the fused backward's data flow (tfoptflow_b200/csrc/bwd_fused.cuh): the A-row layout with its bank
+swizzle, the target-row-indexed workspace K1 writes and K2 reads shifted, the 9-row window and the skewed row-pair
+walk of the consumer.  It is checked against the oracle, so an indexing mistake in the design shows up here, on the
+CPU, before any GPU time is spent; the CUDA code itself is checked by tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+from oracle import pwc_oracle as O
+from tfoptflow_b200 import synth
+
+R, ND, D, TW = 4, 9, 81, 32
+
+
+def a_index(px, d, ex):
+    return d * TW + ((((px >> 2) ^ (ex & 7)) << 2) | (px & 3))
+
+
+def test_a_index_is_a_bijection_and_builder_stores_are_conflict_free():
+    seen = {a_index(px, d, d % ND) for px in range(TW) for d in range(D)}
+    assert seen == set(range(D * TW))
+    # builder: lanes = 4 consecutive pixels x 8 consecutive planes -> 32 distinct banks unless the octet wraps ex 8 -> 0
+    for grp in range(8):
+        for octet in range(10):
+            banks = [a_index(grp * 4 + (l >> 3), octet * 8 + (l & 7), (octet * 8 + (l & 7)) % ND) % 32 for l in range(32)]
+            assert len(set(banks)) >= 28
+
+
+def consumer(A_rows, win, P):
+    """A_rows[j] : [81*32] swizzled planes of band row j; win[u] : [40, C] window rows -> out[j][px][c].
+    Row pair p: half h handles row 2p + h with ey = t - h at step t, window row u = 2p + t (same for both halves)."""
+    C = win.shape[-1]
+    out = np.zeros((2 * P, TW, C), np.float64)
+    for p in range(P):
+        for t in range(ND + 1):
+            u = 2 * p + t
+            for h in range(2):
+                ey = t - h
+                if not 0 <= ey < ND:
+                    continue
+                for ex in range(ND):
+                    a = np.array([A_rows[2 * p + h][a_index(px, ey * ND + ex, ex)] for px in range(TW)])
+                    out[2 * p + h] += a[:, None] * win[u][ex:ex + TW]
+    return out
+
+
+@pytest.mark.parametrize("shape", [(1, 10, 40, 32, 6), (2, 7, 33, 32, 4)])
+def test_model_matches_oracle(shape):
+    B, H, W, C, RB = shape
+    d = synth.make_level(B, H, W, C, 5, np.float32, "smooth", with_grad=True)
+    c1, c2, flow, g = (d[k] for k in ("c1", "c2", "flow", "g"))
+    warp = O.dense_image_warp(c2, flow)
+    outf = O.cost_volume(c1, warp, R)
+    dc1_ref, dwarp_ref = O.cost_volume_bwd(g, outf, c1, warp, R)
+    gp = (g * np.where(outf > 0, 1.0, 0.1)).astype(np.float64) / C
+    nsx = (W + TW - 1) // TW
+    nb = (H + RB - 1) // RB
+    ws = np.full((B, H, nsx, D * TW), np.nan)   # never-written entries must not be used
+    dc1 = np.zeros_like(dc1_ref, dtype=np.float64)
+    dwarp = np.zeros_like(dc1)
+
+    def units():
+        for b in range(B):
+            for band in range(nb):
+                for sx in range(nsx):
+                    y0 = band * RB
+                    rows = min(RB, H - y0)
+                    yield b, sx, sx * TW, y0, rows, (rows + 1) // 2
+
+    def window(src, b, x0, y0, P):
+        win = np.zeros((2 * P + 2 * R, TW + 2 * R, C))
+        for u in range(2 * P + 2 * R):
+            y = y0 - R + u
+            for px in range(TW + 2 * R):
+                x = x0 - R + px
+                if 0 <= y < H and 0 <= x < W:
+                    win[u, px] = src[b, y, x]
+        return win
+
+    # ---- K1
+    for b, sx, x0, y0, rows, P in units():
+        A = np.zeros((2 * P, D * TW))
+        for j in range(rows):
+            for px in range(TW):
+                if x0 + px < W:
+                    for dd in range(D):
+                        A[j][a_index(px, dd, dd % ND)] = gp[b, y0 + j, x0 + px, dd]
+            for dyi in range(ND):   # bulk copies: plane block dyi -> target row y + dyi - 4
+                yq = y0 + j + dyi - R
+                if 0 <= yq < H:
+                    ws[b, yq, sx, dyi * ND * TW:(dyi + 1) * ND * TW] = A[j][dyi * ND * TW:(dyi + 1) * ND * TW]
+        o = consumer(A, window(warp, b, x0, y0, P), P)
+        for j in range(rows):
+            n = min(TW, W - x0)
+            dc1[b, y0 + j, x0:x0 + n] = o[j][:n]
+    # ---- K2
+    for b, sx, x0, y0, rows, P in units():
+        A = np.zeros((2 * P, D * TW))
+        for j in range(rows):
+            y = y0 + j
+            for ey in range(ND):
+                ys = y + ey - R
+                for ex in range(ND):
+                    for px in range(TW):
+                        xs = x0 + px + ex - R
+                        v = 0.0
+                        if 0 <= ys < H and 0 <= xs < W:
+                            dxi = 2 * R - ex
+                            v = ws[b, y, xs >> 5, a_index(xs & 31, (2 * R - ey) * ND + dxi, dxi)]
+                        A[j][a_index(px, ey * ND + ex, ex)] = v
+        assert np.isfinite(A).all(), "K2 read a workspace entry K1 never wrote"
+        o = consumer(A, window(c1, b, x0, y0, P), P)
+        for j in range(rows):
+            n = min(TW, W - x0)
+            dwarp[b, y0 + j, x0:x0 + n] = o[j][:n]
+    assert np.abs(dc1 - dc1_ref).max() <= 2e-6 * np.abs(dc1_ref).max()
+    assert np.abs(dwarp - dwarp_ref).max() <= 2e-6 * np.abs(dwarp_ref).max()

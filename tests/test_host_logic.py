@@ -72,6 +72,21 @@ def _worker(rank, world, port, q):
         ref.append(acc / world)
     out = multi_gpus.average_gradients(grads, bucket_bytes=2048)  # forces several buckets
     ok = all((o is None and e is None) or torch.allclose(o.float(), e, atol=2e-3) for o, e in zip(out, ref))
+    # persistent bucket: per-rank unscale (1/128) + clip to global norm 5.0 BEFORE the mean (model_pwcnet.py:311-314)
+    def tower(rr):
+        gg = torch.Generator().manual_seed(100 + rr)
+        return [torch.randn(50, 4, generator=gg) * 128 * 3, None, torch.randn(333, generator=gg) * 128 * 3]
+    mine = tower(rank)
+    bucket = multi_gpus.GradientBucket(mine)
+    bucket.average(mine, loss_scale=128.0, clip_norm=5.0)
+    exp = None
+    for rr in range(world):
+        t = [x / 128.0 for x in tower(rr) if x is not None]
+        gn = torch.sqrt(sum((x.double() ** 2).sum() for x in t)).float()
+        t = [x * (5.0 / torch.clamp(gn, min=5.0)) for x in t]
+        exp = t if exp is None else [e + x for e, x in zip(exp, t)]
+    exp = [e / world for e in exp]
+    ok = ok and mine[1] is None and all(torch.allclose(o, e, atol=1e-5) for o, e in zip([mine[0], mine[2]], exp))
     # batch sharding covers the batch exactly once across ranks
     lo, hi = multi_gpus.shard_batch(9, rank, world)
     cnt = torch.zeros(9)

@@ -1,0 +1,598 @@
+// Fused backward of warp + cost volume for search_range 4, two launches per level.
+//
+//   g'[p,d]    = g[p,d] * (out[p,d] > 0 ? 1 : 0.1) / C                       (leaky-relu mask, channel mean)
+//   dc1[p,c]   = sum_d g'[p,d]   * warpZ[p + d, c]                           K1
+//   dwarp[q,c] = sum_e g'[q+e,-e] * c1[q + e, c]        (e = -d)             K2
+//   dc2        = bilinear scatter of dwarp, dflow = -(dwarp . d warp/d alpha) * clamp mask * flow_scale   K2
+//
+// Both sums have the same shape: out_row[px][c] = sum_{ey,ex} A[ey][ex][px] * Bwin[row + ey - 4][px + ex - 4][c], a
+// banded correlation of 81 scalar planes A against a 9-row window of feature rows.  One consumer routine serves both:
+//   * a CTA owns (image, 32-pixel strip, band of rows, 32-channel slice) and marches down the band;
+//   * B rows live in a shared-memory ring (K1: rows of c2 warped on the fly by gather warps, never in HBM; K2: rows of c1);
+//   * A rows (81 x 32 fp32 per strip row, [d][px]) live in a second ring.  K1 builds them from g and out, and also
+//     writes them, as they are, to a workspace indexed by TARGET row (9 bulk shared->global copies per row, TMA
+//     `cp.async.bulk`): that is g' transposed for K2, which only has to shift it by ex - 4 pixels when loading;
+//   * 4 consumer warps (one per scheduler) each own a PAIR of output rows: lanes 0-15 row 2p, lanes 16-31 row 2p+1,
+//     8 pixels x 8 channels per lane (32 packed f32x2 accumulators).  The two halves walk the window skewed by one
+//     row, so both read the SAME window row in every step: the B operand (LDS.128, the expensive one) is shared by
+//     the two halves, the A operand is a scalar-broadcast FFMA2 source shared by the 4 channel groups of a pixel group.
+//   * K2 hands finished dwarp rows to 4 scatter warps (red.global.add.v4.f32 into an fp32 dc2, warp-shuffle dflow).
+// Synchronisation: mbarriers only (full per ring slot, done per task); no __syncthreads after the role split.
+#pragma once
+#include "common.cuh"
+
+namespace pwc {
+namespace bwdf {
+
+typedef unsigned long long u64;
+
+constexpr int R = 4, ND = 9, D = 81;
+constexpr int TW = 32;                      // strip width in pixels
+constexpr int KS = 32;                      // channels per CTA
+constexpr int WPX = TW + 2 * R;             // window pixels per row (halo of 4 each side)
+constexpr int WROW = WPX * 8 + WPX / 8;     // float4 per window row: 8 per pixel + 1 pad per 8 pixels
+constexpr int AROW = D * TW / 4;            // float4 per A row
+constexpr int ASLICE = ND * TW / 4;         // float4 per (row, ey) slice
+constexpr int SROW = TW * 8 + TW / 8;       // float4 per staged dwarp row (same padding as the window)
+constexpr int NW = 18;                      // window ring slots: 4 tasks in flight span 16 rows, + 2 ahead
+constexpr int NG = 10;                      // A ring slots: 4 tasks x 2 rows in flight, + 2 ahead
+constexpr int NT = 16;                      // task-done barriers
+constexpr int NDS = 4;                      // staged dwarp rows (one per scatter warp)
+constexpr int NCW = 4, NAW = 4;             // consumer / A-producer warps
+constexpr int NTHREADS = 512;
+constexpr int REGS_CONSUMER = 200, REGS_OTHER = 104;   // 128 * 200 + 384 * 104 = 512 * 128
+
+constexpr size_t OFF_W = 0;
+constexpr size_t OFF_A = OFF_W + (size_t)NW * WROW * 16;
+constexpr size_t OFF_Z = OFF_A + (size_t)NG * AROW * 16;
+constexpr size_t OFF_S = OFF_Z + (size_t)ASLICE * 16;
+constexpr size_t OFF_BAR = OFF_S + (size_t)NDS * SROW * 16;
+constexpr int NBAR = NW + NG + NT + 2 * NDS;
+constexpr size_t SMEM_BYTES = OFF_BAR + (size_t)NBAR * 8;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+
+struct Args {
+  const void* g;        // K1: upstream gradient [B,H,W,81]
+  const void* out;      // K1: forward result    [B,H,W,81]
+  const void* feat;     // K1: c2 (warped on the fly)   K2: c1
+  const void* c2;       // K2: corners for dflow
+  const void* flow;     // NULL = no warp
+  void* dst;            // K1: dc1   K2 without flow: dc2
+  float* acc;           // K2 with flow: fp32 dc2 accumulator (zeroed)
+  void* dflow;          // K2 with flow, single slice: flow gradient
+  float* dflow_acc;     // K2 with flow, several slices: fp32 accumulator (zeroed)
+  float* ws;            // transposed g' workspace [B][H][nsx][81][32]
+  int B, H, W, C;
+  int nsx, nbands, RB, nslices;
+  float flow_scale, inv_c;
+};
+
+// ---- mbarrier / bulk-copy helpers ------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// TMA bulk copy shared -> global (SASS: UBLKCP), tracked by the bulk async-group of the issuing thread
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_read() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// scalar x packed pair (ptxas folds the {a, a} pair into FFMA2's scalar-broadcast operand form)
+__device__ __forceinline__ void ffma2s(u64& d, float a, u64 b) {
+  u64 aa;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(aa), "l"(b));
+}
+__device__ __forceinline__ float2 unpack2(u64 v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ float comp(const float4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+
+// float index of (pixel px, plane d) inside an A row: [d][px], the 8 float4 groups of a plane XOR-ed with (d % 9) & 7 so
+// that the builder's stores (lanes = 4 pixels x 8 consecutive planes) hit 32 distinct banks
+__device__ __forceinline__ int a_index(int px, int d, int ex) { return d * TW + ((((px >> 2) ^ (ex & 7)) << 2) | (px & 3)); }
+
+template <typename T>
+__device__ __forceinline__ float ld1(const T* p) { return ElemTraits<T>::to_f(__ldg(p)); }
+template <>
+__device__ __forceinline__ float ld1<__half>(const __half* p) {
+  return __half2float(__ushort_as_half(__ldg(reinterpret_cast<const unsigned short*>(p))));
+}
+template <>
+__device__ __forceinline__ float ld1<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __uint_as_float((unsigned)__ldg(reinterpret_cast<const unsigned short*>(p)) << 16);
+}
+
+// 8 consecutive channels -> global, in the tensor dtype
+__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
+  st4(p, make_float4(v[0], v[1], v[2], v[3]));
+  st4(p + 4, make_float4(v[4], v[5], v[6], v[7]));
+}
+template <typename T>
+__device__ __forceinline__ void st8(T* p, const float (&v)[8]) {  // 16-bit: one 16-byte store
+  uint4 u;
+  uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const T lo = ElemTraits<T>::from_f(v[2 * k]), hi = ElemTraits<T>::from_f(v[2 * k + 1]);
+    w[k] = (uint32_t)(*reinterpret_cast<const unsigned short*>(&lo)) |
+           ((uint32_t)(*reinterpret_cast<const unsigned short*>(&hi)) << 16);
+  }
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+struct Unit {
+  int b, x0, y0, rows, P, U, cs, sx;   // rows = valid rows of the band, P = row pairs, U = window rows
+};
+
+// wait until every task that reads window row `uold` has finished (tasks are spread round-robin over the NCW consumer
+// warps and complete in order per warp, so the last NCW task indices cover "all tasks <= plast")
+__device__ __forceinline__ void wait_window_free(uint64_t* done, int uold, int P) {
+  int plast = uold >> 1;
+  if (plast > P - 1) plast = P - 1;
+#pragma unroll
+  for (int k = 0; k < NCW; ++k) {
+    const int p = plast - k;
+    if (p >= 0) mbar_wait(&done[p % NT], (p / NT) & 1);
+  }
+}
+
+// ---- B producers -------------------------------------------------------------------------------
+// window row u <-> image row y0 - 4 + u, pixels x0 - 4 .. x0 + 35, channels [32 cs, 32 cs + 32); zero outside the image.
+// 8 lanes per pixel (one float4 each), 4 pixels per step, 10 steps per row.  The flow of all 10 steps is loaded and
+// turned into corner indices / weights first (one latency exposure), then the corners are gathered GB steps at a time.
+template <bool WARP, int NPROD, typename T, typename TF>
+__device__ __forceinline__ void produce_window(const Args& a, const Unit& un, float4* sW, uint64_t* full_w,
+                                               uint64_t* done, int pi, int lane) {
+  const T* __restrict__ feat = reinterpret_cast<const T*>(a.feat);
+  const TF* __restrict__ flow = reinterpret_cast<const TF*>(a.flow);
+  const int psub = lane >> 3, f4 = lane & 7;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  constexpr int NIT = WPX / 4;           // 10
+  constexpr int GB = WARP ? 2 : 5;       // steps per gather batch (8 / 5 LDG.128 in flight per lane)
+  const T* base = feat + (size_t)un.cs * KS + 4 * f4;
+  for (int u = pi; u < un.U; u += NPROD) {
+    if (u >= NW) wait_window_free(done, u - NW, un.P);
+    float4* Wd = sW + (size_t)(u % NW) * WROW;
+    const int y = un.y0 - R + u;
+    if (y < 0 || y >= a.H) {
+      for (int i = lane; i < WROW; i += 32) Wd[i] = zero;
+    } else {
+      int pix[NIT];
+      float wx[NIT], wy[NIT];
+      unsigned inmask = 0;
+      {
+        TF f0[NIT], f1[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+          const int x = un.x0 - R + it * 4 + psub;
+          const bool in = x >= 0 && x < a.W;
+          inmask |= in ? (1u << it) : 0u;
+          const int xc = min(max(x, 0), a.W - 1);
+          pix[it] = (un.b * a.H + y) * a.W + xc;
+          if (WARP) {
+            f0[it] = flow[2 * (size_t)pix[it]];
+            f1[it] = flow[2 * (size_t)pix[it] + 1];
+          }
+        }
+        if (WARP) {
+#pragma unroll
+          for (int it = 0; it < NIT; ++it) {
+            const int x = un.x0 - R + it * 4 + psub;
+            const int xc = min(max(x, 0), a.W - 1);
+            const SampleCoord s = sample_coord_v<T, TF>(f0[it], f1[it], a.flow_scale, un.b, y, xc, a.H, a.W);
+            pix[it] = s.pix;
+            wx[it] = s.ax;
+            wy[it] = s.ay;
+          }
+        }
+      }
+#pragma unroll
+      for (int it0 = 0; it0 < NIT; it0 += GB) {
+        float4 tl[GB], tr[GB], bl[GB], br[GB];
+#pragma unroll
+        for (int k = 0; k < GB; ++k) {
+          const T* q = base + (size_t)pix[it0 + k] * a.C;
+          tl[k] = ld4(q);
+          if (WARP) {
+            tr[k] = ld4(q + a.C);
+            bl[k] = ld4(q + (size_t)a.W * a.C);
+            br[k] = ld4(q + (size_t)a.W * a.C + a.C);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < GB; ++k) {
+          const int it = it0 + k, px = it * 4 + psub;
+          float4 v = tl[k];
+          if (WARP) {
+            if (ElemTraits<T>::kIsHalf) {
+              v = round4<T>(bilerp4(tl[k], tr[k], bl[k], br[k], wx[it], wy[it]));  // the reference's warp is a 16-bit tensor
+            } else {
+              const float w11 = wx[it] * wy[it], w01 = wx[it] - w11, w10 = wy[it] - w11, w00 = (1.0f - wx[it]) - w10;
+              v.x = fmaf(w11, br[k].x, fmaf(w10, bl[k].x, fmaf(w01, tr[k].x, w00 * tl[k].x)));
+              v.y = fmaf(w11, br[k].y, fmaf(w10, bl[k].y, fmaf(w01, tr[k].y, w00 * tl[k].y)));
+              v.z = fmaf(w11, br[k].z, fmaf(w10, bl[k].z, fmaf(w01, tr[k].z, w00 * tl[k].z)));
+              v.w = fmaf(w11, br[k].w, fmaf(w10, bl[k].w, fmaf(w01, tr[k].w, w00 * tl[k].w)));
+            }
+          }
+          Wd[px * 8 + (px >> 3) + f4] = ((inmask >> it) & 1u) ? v : zero;
+        }
+      }
+    }
+    mbar_arrive(&full_w[u % NW]);
+  }
+}
+
+// ---- A producers -------------------------------------------------------------------------------
+// K1: A[d][px] = g * mask / C for strip row j, then the 9 target-row slices go to the workspace by TMA
+template <typename T>
+__device__ __forceinline__ void produce_a_k1(const Args& a, const Unit& un, float* sA, uint64_t* full_a, uint64_t* done,
+                                             int ai, int lane) {
+  const T* __restrict__ g = reinterpret_cast<const T*>(a.g);
+  const T* __restrict__ out = reinterpret_cast<const T*>(a.out);
+  const int psub = lane >> 3, dq = lane & 7;
+  for (int j = ai; j < 2 * un.P; j += NAW) {
+    if (j >= NG) {
+      const int p = (j - NG) >> 1;
+      mbar_wait(&done[p % NT], (p / NT) & 1);
+    }
+    float* A = sA + (size_t)(j % NG) * (AROW * 4);
+    const int y = un.y0 + j;
+    if (j >= un.rows) {
+      for (int i = lane; i < AROW; i += 32) reinterpret_cast<float4*>(A)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      const size_t rowpix = ((size_t)un.b * a.H + y) * a.W + un.x0;
+#pragma unroll 1
+      for (int grp = 0; grp < TW / 4; grp += 2) {   // 2 groups x 11 plane octets x (g, out): 44 loads in flight per lane
+        float gv[2][11], ov[2][11];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int px = (grp + q) * 4 + psub;
+          const bool pin = un.x0 + px < a.W;
+          const T* gp = g + (rowpix + px) * D;
+          const T* op = out + (rowpix + px) * D;
+#pragma unroll
+          for (int o = 0; o < 11; ++o) {
+            const int d = o * 8 + dq;
+            const bool ok = pin && d < D;
+            gv[q][o] = ok ? ld1<T>(gp + d) : 0.f;
+            ov[q][o] = ok ? ld1<T>(op + d) : 1.f;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int px = (grp + q) * 4 + psub;
+#pragma unroll
+          for (int o = 0; o < 11; ++o) {
+            const int d = o * 8 + dq;
+            if (d < D) A[a_index(px, d, d % ND)] = (gv[q][o] * (ov[q][o] > 0.0f ? 1.0f : 0.1f)) * a.inv_c;
+          }
+        }
+      }
+    }
+    if (j < un.rows) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my stores, before TMA reads them
+    __syncwarp();
+    if (j < un.rows) {
+      if (lane < ND) {
+        const int yq = y + lane - R;  // plane block dyi = lane lands in target row y + dyi - 4
+        if (yq >= 0 && yq < a.H)
+          bulk_s2g(a.ws + ((((size_t)un.b * a.H + yq) * a.nsx + un.sx) * D + lane * ND) * TW, A + lane * ND * TW,
+                   ND * TW * 4);
+        bulk_commit_wait_read();
+      }
+      __syncwarp();
+    }
+    mbar_arrive(&full_a[j % NG]);
+  }
+}
+
+// K2: A[ey][ex][px] = g' of the source pixel (row + ey - 4, x + ex - 4) for displacement (8 - ey, 8 - ex),
+// read from the workspace rows of target row y (written by K1 of whichever CTA owned the source rows)
+__device__ __forceinline__ void produce_a_k2(const Args& a, const Unit& un, float* sA, uint64_t* full_a, uint64_t* done,
+                                             int ai, int lane) {
+  for (int j = ai; j < 2 * un.P; j += NAW) {
+    if (j >= NG) {
+      const int p = (j - NG) >> 1;
+      mbar_wait(&done[p % NT], (p / NT) & 1);
+    }
+    float* A = sA + (size_t)(j % NG) * (AROW * 4);
+    const int y = un.y0 + j;
+    if (j >= un.rows) {
+      for (int i = lane; i < AROW; i += 32) reinterpret_cast<float4*>(A)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      const float* __restrict__ wrow = a.ws + ((size_t)un.b * a.H + y) * a.nsx * (D * TW);
+#pragma unroll 1
+      for (int ey0 = 0; ey0 < ND; ey0 += 3) {   // 27 loads in flight per lane
+        float v[3][ND];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const int ey = ey0 + q, ys = y + ey - R;
+          const bool rv = ys >= 0 && ys < a.H;
+#pragma unroll
+          for (int ex = 0; ex < ND; ++ex) {
+            const int xs = un.x0 + lane + ex - R;
+            v[q][ex] = 0.f;
+            if (rv && xs >= 0 && xs < a.W) {
+              const int dxi = 2 * R - ex;
+              v[q][ex] = __ldg(wrow + (size_t)(xs >> 5) * (D * TW) + a_index(xs & 31, (2 * R - ey) * ND + dxi, dxi));
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+          for (int ex = 0; ex < ND; ++ex) A[a_index(lane, (ey0 + q) * ND + ex, ex)] = v[q][ex];
+      }
+    }
+    mbar_arrive(&full_a[j % NG]);
+  }
+}
+
+// ---- consumer ----------------------------------------------------------------------------------
+// MODE 0: K1, store dc1.  MODE 1: K2; without a flow the rows are dc2 and are stored, with a flow they are staged for
+// the scatter warps.
+template <int MODE, bool HAS_FLOW, typename T>
+__device__ __forceinline__ void consume(const Args& a, const Unit& un, const float4* sW, const float4* sA,
+                                        const float4* sZ, float4* sS, uint64_t* full_w, uint64_t* full_a,
+                                        uint64_t* done, uint64_t* full_d, uint64_t* empty_d, int warp, int lane) {
+  const int h = lane >> 4, s = lane & 15, pg = s >> 2, cg = s & 3;
+  const int g0 = 2 * pg, g1 = 2 * pg + 1;
+  for (int p = warp; p < un.P; p += NCW) {
+    mbar_wait(&full_a[(2 * p) % NG], ((2 * p) / NG) & 1);
+    mbar_wait(&full_a[(2 * p + 1) % NG], ((2 * p + 1) / NG) & 1);
+    const float4* Abase = sA + (size_t)((2 * p + h) % NG) * AROW;
+    u64 acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[i][q] = 0ull;
+
+#pragma unroll 1
+    for (int t = 0; t < ND + 1; ++t) {
+      const int u = 2 * p + t;
+      mbar_wait(&full_w[u % NW], (u / NW) & 1);
+      const ulonglong2* Wr = reinterpret_cast<const ulonglong2*>(sW + (size_t)(u % NW) * WROW + pg * 65 + 2 * cg);
+      const int ey = t - h;  // the two halves use the same window row for different displacements
+      const float4* Ar = (ey >= 0 && ey < ND) ? Abase + ey * ASLICE : sZ;
+      float4 a0[ND], a1[ND];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (j < ND) a0[j] = Ar[j * 8 + (g0 ^ (j & 7))];
+        if (j >= 4 && j - 4 < ND) a1[j - 4] = Ar[(j - 4) * 8 + (g1 ^ ((j - 4) & 7))];
+        const ulonglong2 b0 = Wr[j * 8 + (j >> 3)], b1 = Wr[j * 8 + (j >> 3) + 1];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int ex = j - i;
+          if (ex >= 0 && ex < ND) {
+            const float av = i < 4 ? comp(a0[ex], i) : comp(a1[ex], i - 4);
+            ffma2s(acc[i][0], av, b0.x);
+            ffma2s(acc[i][1], av, b0.y);
+            ffma2s(acc[i][2], av, b1.x);
+            ffma2s(acc[i][3], av, b1.y);
+          }
+        }
+      }
+    }
+
+    // epilogue: row j of the band, pixels x0 + 8 pg .. + 7, channels 32 cs + 8 cg .. + 7
+    const int j = 2 * p + h;
+    const bool rowv = j < un.rows;
+    if (MODE == 1 && HAS_FLOW) {
+      const int slot = j % NDS, k = j / NDS;
+      if (rowv) {
+        if (k > 0) mbar_wait(&empty_d[slot], (k - 1) & 1);
+        float4* S = sS + (size_t)slot * SROW + pg * 65 + 2 * cg;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 v0 = unpack2(acc[i][0]), v1 = unpack2(acc[i][1]), v2 = unpack2(acc[i][2]), v3 = unpack2(acc[i][3]);
+          S[i * 8] = make_float4(v0.x, v0.y, v1.x, v1.y);
+          S[i * 8 + 1] = make_float4(v2.x, v2.y, v3.x, v3.y);
+        }
+        mbar_arrive(&full_d[slot]);
+      }
+    } else if (rowv) {
+      T* dst = reinterpret_cast<T*>(a.dst) +
+               (((size_t)un.b * a.H + un.y0 + j) * a.W + un.x0 + 8 * pg) * a.C + un.cs * KS + 8 * cg;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (un.x0 + 8 * pg + i < a.W) {
+          const float2 v0 = unpack2(acc[i][0]), v1 = unpack2(acc[i][1]), v2 = unpack2(acc[i][2]), v3 = unpack2(acc[i][3]);
+          const float v[8] = {v0.x, v0.y, v1.x, v1.y, v2.x, v2.y, v3.x, v3.y};
+          st8(dst + (size_t)i * a.C, v);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&done[p % NT]);
+  }
+}
+
+// ---- K2 scatter warps ----------------------------------------------------------------------------
+// dense_image_warp backward for one staged dwarp row: 8 lanes per pixel (4 channels each), 4 pixels per step
+template <typename T, typename TF>
+__device__ __forceinline__ void scatter_rows(const Args& a, const Unit& un, const float4* sS, uint64_t* full_d,
+                                             uint64_t* empty_d, int sw, int lane) {
+  const T* __restrict__ c2 = reinterpret_cast<const T*>(a.c2);
+  const TF* __restrict__ flow = reinterpret_cast<const TF*>(a.flow);
+  const int psub = lane >> 3, f4 = lane & 7;
+  for (int j = sw; j < un.rows; j += NDS) {
+    mbar_wait(&full_d[sw], (j / NDS) & 1);
+    const float4* S = sS + (size_t)sw * SROW;
+    const int y = un.y0 + j;
+#pragma unroll 2
+    for (int it = 0; it < TW / 4; ++it) {
+      const int px = it * 4 + psub, x = un.x0 + px;
+      const bool valid = x < a.W;
+      const int xc = valid ? x : a.W - 1;
+      const SampleCoord sc = sample_coord<T, TF>(flow, a.flow_scale, un.b, y, xc, a.H, a.W);
+      const float ax = sc.ax, ay = sc.ay;
+      const size_t i_tl = (size_t)sc.pix * a.C + un.cs * KS + 4 * f4, i_tr = i_tl + a.C;
+      const size_t i_bl = i_tl + (size_t)a.W * a.C, i_br = i_bl + a.C;
+      float dax = 0.f, day = 0.f;
+      if (valid) {
+        const float4 tl = ld4(c2 + i_tl), tr = ld4(c2 + i_tr), bl = ld4(c2 + i_bl), br = ld4(c2 + i_br);
+        const float4 gw = S[px * 8 + (px >> 3) + f4];
+        const float w_tl = (1.f - ay) * (1.f - ax), w_tr = (1.f - ay) * ax, w_bl = ay * (1.f - ax), w_br = ay * ax;
+        atomicAdd(reinterpret_cast<float4*>(a.acc + i_tl), make_float4(gw.x * w_tl, gw.y * w_tl, gw.z * w_tl, gw.w * w_tl));
+        atomicAdd(reinterpret_cast<float4*>(a.acc + i_tr), make_float4(gw.x * w_tr, gw.y * w_tr, gw.z * w_tr, gw.w * w_tr));
+        atomicAdd(reinterpret_cast<float4*>(a.acc + i_bl), make_float4(gw.x * w_bl, gw.y * w_bl, gw.z * w_bl, gw.w * w_bl));
+        atomicAdd(reinterpret_cast<float4*>(a.acc + i_br), make_float4(gw.x * w_br, gw.y * w_br, gw.z * w_br, gw.w * w_br));
+        const float gv[4] = {gw.x, gw.y, gw.z, gw.w};
+        const float vtl[4] = {tl.x, tl.y, tl.z, tl.w}, vtr[4] = {tr.x, tr.y, tr.z, tr.w};
+        const float vbl[4] = {bl.x, bl.y, bl.z, bl.w}, vbr[4] = {br.x, br.y, br.z, br.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float top = ax * (vtr[i] - vtl[i]) + vtl[i];
+          const float bot = ax * (vbr[i] - vbl[i]) + vbl[i];
+          dax = fmaf(gv[i], (1.f - ay) * (vtr[i] - vtl[i]) + ay * (vbr[i] - vbl[i]), dax);
+          day = fmaf(gv[i], bot - top, day);
+        }
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        dax += __shfl_xor_sync(0xffffffffu, dax, o);
+        day += __shfl_xor_sync(0xffffffffu, day, o);
+      }
+      if (valid && f4 == 0) {
+        const size_t pidx = ((size_t)un.b * a.H + y) * a.W + x;
+        const float d0 = -day * sc.my * a.flow_scale, d1 = -dax * sc.mx * a.flow_scale;
+        if (a.dflow_acc != nullptr) {
+          atomicAdd(a.dflow_acc + 2 * pidx, d0);
+          atomicAdd(a.dflow_acc + 2 * pidx + 1, d1);
+        } else {
+          TF* df = reinterpret_cast<TF*>(a.dflow);
+          df[2 * pidx] = ElemTraits<TF>::from_f(d0);
+          df[2 * pidx + 1] = ElemTraits<TF>::from_f(d1);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_d[sw]);
+  }
+}
+
+// ---- the kernel -----------------------------------------------------------------------------------
+template <int MODE, bool HAS_FLOW, typename T, typename TF>
+__global__ void __launch_bounds__(NTHREADS, 1) bwd_fused_kernel(const Args a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float4* sW = reinterpret_cast<float4*>(smem + OFF_W);
+  float4* sA = reinterpret_cast<float4*>(smem + OFF_A);
+  float4* sZ = reinterpret_cast<float4*>(smem + OFF_Z);
+  float4* sS = reinterpret_cast<float4*>(smem + OFF_S);
+  uint64_t* full_w = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* full_a = full_w + NW;
+  uint64_t* done = full_a + NG;
+  uint64_t* full_d = done + NT;
+  uint64_t* empty_d = full_d + NDS;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  Unit un;
+  {
+    int id = blockIdx.x;
+    un.cs = id % a.nslices; id /= a.nslices;
+    un.sx = id % a.nsx; id /= a.nsx;
+    const int band = id % a.nbands;
+    un.b = id / a.nbands;
+    un.x0 = un.sx * TW;
+    un.y0 = band * a.RB;
+    un.rows = min(a.RB, a.H - un.y0);
+    un.P = (un.rows + 1) >> 1;
+    un.U = 2 * un.P + 2 * R;
+  }
+  if (tid == 0) {
+    for (int i = 0; i < NW; ++i) mbar_init(&full_w[i], 32);
+    for (int i = 0; i < NG; ++i) mbar_init(&full_a[i], 32);
+    for (int i = 0; i < NT; ++i) mbar_init(&done[i], 1);
+    for (int i = 0; i < NDS; ++i) { mbar_init(&full_d[i], 16); mbar_init(&empty_d[i], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < ASLICE; i += NTHREADS) sZ[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+
+  if (warp < NCW) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_CONSUMER));
+    consume<MODE, HAS_FLOW, T>(a, un, sW, sA, sZ, sS, full_w, full_a, done, full_d, empty_d, warp, lane);
+    return;
+  }
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_OTHER));
+  if (warp < NCW + NAW) {
+    if (MODE == 0) produce_a_k1<T>(a, un, reinterpret_cast<float*>(sA), full_a, done, warp - NCW, lane);
+    else produce_a_k2(a, un, reinterpret_cast<float*>(sA), full_a, done, warp - NCW, lane);
+    return;
+  }
+  if (MODE == 0) {  // 8 window producers: the bilinear gather is the heavy producer of K1
+    produce_window<HAS_FLOW, 8, T, TF>(a, un, sW, full_w, done, warp - NCW - NAW, lane);
+  } else if (warp < NCW + NAW + 4) {
+    produce_window<false, 4, T, TF>(a, un, sW, full_w, done, warp - NCW - NAW, lane);
+  } else if (HAS_FLOW) {
+    scatter_rows<T, TF>(a, un, sS, full_d, empty_d, warp - NCW - NAW - 4, lane);
+  }
+}
+
+// Workspace: transposed g' (fp32), then - with a flow - an fp32 dc2 accumulator for 16-bit tensors and an fp32 dflow
+// accumulator when the channels are processed in several slices.
+struct Plan {
+  int nsx, nbands, RB, nslices;
+  size_t ws_off, acc_off, dflow_off, total;
+  bool acc_in_ws, dflow_in_ws;
+};
+inline size_t up256(size_t n) { return (n + 255) & ~size_t(255); }
+
+inline Plan make_plan(int B, int H, int W, int C, size_t elt, size_t flow_elt, bool has_flow, int sms) {
+  Plan p{};
+  p.nsx = (W + TW - 1) / TW;
+  p.nslices = C / KS;
+  const long long base = (long long)B * p.nsx * p.nslices;
+  long long nb = base > 0 ? (6LL * sms + base - 1) / base : 1;
+  const long long nbmax = H / 14 > 1 ? H / 14 : 1;  // bands shorter than 14 rows pay > 1.5x on the window rows
+  if (nb > nbmax) nb = nbmax;
+  if (nb < 1) nb = 1;
+  int rb = (int)((H + nb - 1) / nb);
+  rb += rb & 1;
+  p.RB = rb;
+  p.nbands = (H + rb - 1) / rb;
+  size_t off = 0;
+  p.ws_off = off;
+  off += up256((size_t)B * H * p.nsx * D * TW * 4);
+  p.acc_in_ws = has_flow && elt != 4;
+  p.acc_off = off;
+  if (p.acc_in_ws) off += up256((size_t)B * H * W * C * 4);
+  p.dflow_in_ws = has_flow && p.nslices > 1 && flow_elt != 4;
+  p.dflow_off = off;
+  if (p.dflow_in_ws) off += up256((size_t)B * H * W * 2 * 4);
+  p.total = off;
+  return p;
+}
+
+inline bool covered(int C, int r, int64_t gps, int64_t ops, const void* c1, const void* c2, const void* dc1,
+                    const void* dc2, size_t elt) {
+  (void)elt;
+  auto al = [&](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
+  return r == R && C % KS == 0 && gps == D && ops == D && al(c1) && al(c2) && al(dc1) && al(dc2);
+}
+
+}  // namespace bwdf
+}  // namespace pwc

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "bwd.cuh"
+#include "bwd_fused.cuh"
 #include "common.cuh"
 #include "fwd_generic.cuh"
 #include "fwd_tile.cuh"
@@ -32,8 +33,11 @@ std::atomic<int> g_stream_dbg{0};
 constexpr int kTallMinH = 28;
 std::atomic<int> g_overlap{1};
 std::atomic<int> g_bwd_tiled{1};
+std::atomic<int> g_bwd_impl{0};   // 0 = auto, 1 = unfused v1 kernels, 2 = fused kernels (error when not covered)
 std::atomic<int> g_tile_small{1};
 std::atomic<int> g_side_reverse{1};
+std::atomic<int> g_side_sms{16};          // SMs the tall levels' persistent kernels leave to the short levels of a pyramid pass
+thread_local int t_reserve_sms = 0;
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -143,8 +147,10 @@ int fwd_typed(const void* c1, const void* c2, const void* flow, float flow_scale
     // instantiated for the dtype pairs the reference uses (fp32/fp32, fp16/fp16); others take the tiled kernel
     if constexpr ((std::is_same<T, float>::value && std::is_same<TF, float>::value) ||
                   (std::is_same<T, __half>::value && std::is_same<TF, __half>::value)) {
+      int ctas = g_stream_ctas.load();
+      if (ctas <= 0 && t_reserve_sms > 0 && t_reserve_sms < dev.sms) ctas = dev.sms - t_reserve_sms;
       rc = pwc::stream::launch<T, TF>((const T*)c1, (const T*)c2, (const TF*)flow, flow_scale, (T*)out, B, H, W, C,
-                                      ops, st, dev.sms, g_stream_ctas.load(), g_stream_pf.load(), g_stream_dbg.load());
+                                      ops, st, dev.sms, ctas, g_stream_pf.load(), g_stream_dbg.load());
     }
     if (rc == 0) { PWC_LAUNCH_CHECK(); return PWC_OK; }
     if (rc < 0) return fail(PWC_ERR_CUDA, "stream kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -334,10 +340,70 @@ int cv_bwd_typed(const void* g, const void* out, const void* c1, const void* war
   return bwd_corr_launch<1, T, T>(g, out, c1, dwarp, B, H, W, C, r, gps, ops, st, dev);
 }
 
+// Fused backward (bwd_fused.cuh): K1 = dc1 + transposed g' workspace, K2 = dwarp -> dc2 / dflow.  Two kernel launches
+// per level (plus a memset of the scatter target, and a cast for 16-bit tensors).
+template <typename T, typename TF>
+int bwd_fused_launch(const void* g, const void* out, const void* c1, const void* c2, const void* flow, float scale,
+                     void* dc1, void* dc2, void* dflow, int B, int H, int W, int C, void* ws, size_t ws_bytes,
+                     cudaStream_t st, const DevInfo& dev) {
+  namespace bf = pwc::bwdf;
+  const bool hf = flow != nullptr;
+  const bf::Plan pl = bf::make_plan(B, H, W, C, sizeof(T), sizeof(TF), hf, dev.sms);
+  if (ws_bytes < pl.total || ws == nullptr)
+    return fail(PWC_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", pl.total, ws_bytes);
+  if (!aligned(ws, 256)) return fail(PWC_ERR_ALIGN, "workspace must be 256-byte aligned");
+  char* base = (char*)ws;
+  const size_t n = (size_t)B * H * W * C, npix = (size_t)B * H * W;
+  bf::Args a{};
+  a.g = g; a.out = out; a.flow = flow; a.c2 = c2;
+  a.ws = (float*)(base + pl.ws_off);
+  a.B = B; a.H = H; a.W = W; a.C = C;
+  a.nsx = pl.nsx; a.nbands = pl.nbands; a.RB = pl.RB; a.nslices = pl.nslices;
+  a.flow_scale = scale; a.inv_c = 1.0f / (float)C;
+  const long long grid = (long long)B * pl.nbands * pl.nsx * pl.nslices;
+  if (grid >= (1LL << 31)) return fail(PWC_ERR_BAD_SHAPE, "too many strips");
+  auto prep = [&](auto kern) -> int {
+    PWC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf::SMEM_BYTES));
+    return PWC_OK;
+  };
+  auto k1 = hf ? bf::bwd_fused_kernel<0, true, T, TF> : bf::bwd_fused_kernel<0, false, T, TF>;
+  auto k2 = hf ? bf::bwd_fused_kernel<1, true, T, TF> : bf::bwd_fused_kernel<1, false, T, TF>;
+  int rc = prep(k1);
+  if (rc) return rc;
+  if ((rc = prep(k2))) return rc;
+  float* acc = nullptr;
+  float* dfacc = nullptr;
+  if (hf) {
+    acc = pl.acc_in_ws ? (float*)(base + pl.acc_off) : (float*)dc2;
+    PWC_CUDA(cudaMemsetAsync(acc, 0, n * 4, st));
+    if (pl.nslices > 1) {
+      dfacc = pl.dflow_in_ws ? (float*)(base + pl.dflow_off) : (float*)dflow;
+      PWC_CUDA(cudaMemsetAsync(dfacc, 0, npix * 2 * 4, st));
+    }
+  }
+  a.feat = c2; a.dst = dc1;
+  k1<<<(unsigned)grid, bf::NTHREADS, bf::SMEM_BYTES, st>>>(a);
+  PWC_LAUNCH_CHECK();
+  a.feat = c1; a.dst = dc2; a.acc = acc; a.dflow = dflow; a.dflow_acc = dfacc;
+  k2<<<(unsigned)grid, bf::NTHREADS, bf::SMEM_BYTES, st>>>(a);
+  PWC_LAUNCH_CHECK();
+  if (hf && pl.acc_in_ws && (rc = cast_launch<T>(acc, dc2, (int64_t)n, st, dev))) return rc;
+  if (hf && dfacc && pl.dflow_in_ws && (rc = cast_launch<TF>(dfacc, dflow, (int64_t)npix * 2, st, dev))) return rc;
+  return PWC_OK;
+}
+
 template <typename T, typename TF>
 int fused_bwd_typed(const void* g, const void* out, const void* c1, const void* c2, const void* flow, float scale,
                     void* dc1, void* dc2, void* dflow, int B, int H, int W, int C, int r, int dtype, int64_t gps,
                     int64_t ops, void* ws, size_t ws_bytes, cudaStream_t st, const DevInfo& dev) {
+  {
+    const int impl = g_bwd_impl.load();
+    const bool ok = pwc::bwdf::covered(C, r, gps, ops, c1, c2, dc1, dc2, sizeof(T));
+    if (impl == 2 && !ok)
+      return fail(PWC_ERR_BAD_ARG, "bwd_impl=2: the fused backward needs r == 4, C %% 32 == 0, dense g / out and 16-byte aligned tensors");
+    if (impl != 1 && ok)
+      return bwd_fused_launch<T, TF>(g, out, c1, c2, flow, scale, dc1, dc2, dflow, B, H, W, C, ws, ws_bytes, st, dev);
+  }
   if (flow == nullptr) return cv_bwd_typed<T>(g, out, c1, c2, dc1, dc2, B, H, W, C, r, gps, ops, st, dev);
   const BwdWs L = bwd_ws_layout(B, H, W, C, dtype, true);
   if (ws_bytes < L.total || ws == nullptr)
@@ -407,12 +473,22 @@ int pwc_set_option(const char* key, int value) {
     g_overlap.store(value);
     return PWC_OK;
   }
+  if (!strcmp(key, "bwd_impl")) {
+    if (value < 0 || value > 2) return fail(PWC_ERR_BAD_ARG, "bwd_impl must be 0..2");
+    g_bwd_impl.store(value);
+    return PWC_OK;
+  }
   if (!strcmp(key, "bwd_tiled")) {  // 0: one-pixel-per-thread backward correlation kernels
     g_bwd_tiled.store(value);
     return PWC_OK;
   }
   if (!strcmp(key, "side_reverse")) {  // order in which the short levels are launched on the side streams
     g_side_reverse.store(value);
+    return PWC_OK;
+  }
+  if (!strcmp(key, "side_sms")) {  // SMs left to the short levels while the tall levels' persistent kernels run
+    if (value < 0 || value > 64) return fail(PWC_ERR_BAD_ARG, "side_sms must be 0..64");
+    g_side_sms.store(value);
     return PWC_OK;
   }
   if (!strcmp(key, "tile_small")) {  // 0: always the 8x32 tile shape
@@ -445,6 +521,11 @@ int pwc_get_option(const char* key, int* value) {
   if (!strcmp(key, "stream_prefetch")) { *value = g_stream_pf.load(); return PWC_OK; }
   if (!strcmp(key, "stream_debug")) { *value = g_stream_dbg.load(); return PWC_OK; }
   if (!strcmp(key, "overlap_levels")) { *value = g_overlap.load(); return PWC_OK; }
+  if (!strcmp(key, "bwd_impl")) { *value = g_bwd_impl.load(); return PWC_OK; }
+  if (!strcmp(key, "side_sms")) { *value = g_side_sms.load(); return PWC_OK; }
+  if (!strcmp(key, "bwd_tiled")) { *value = g_bwd_tiled.load(); return PWC_OK; }
+  if (!strcmp(key, "side_reverse")) { *value = g_side_reverse.load(); return PWC_OK; }
+  if (!strcmp(key, "tile_small")) { *value = g_tile_small.load(); return PWC_OK; }
   return fail(PWC_ERR_BAD_ARG, "unknown option '%s'", key);
 }
 
@@ -493,40 +574,63 @@ SideStreams* side_streams_for_device() {
 int pwc_pyramid_fwd(const pwc_level_t* levels, int n_levels, int B, int r, int dtype, int flow_dtype,
                     void* cuda_stream) {
   if (n_levels < 0 || (n_levels > 0 && !levels)) return fail(PWC_ERR_BAD_ARG, "bad level list");
-  cudaStream_t main_st = (cudaStream_t)cuda_stream;
-  SideStreams* S = (n_levels > 1 && g_overlap.load()) ? side_streams_for_device() : nullptr;
-  int n_side = 0;
-  bool used[3] = {false, false, false};
-  // tall levels first, in order, on the caller's stream (their persistent kernels want every SM) ...
+  // every level is validated before anything is launched, so a bad argument cannot leave forked work behind
+  if (!dtype_ok(dtype) || !dtype_ok(flow_dtype)) return fail(PWC_ERR_BAD_DTYPE, "unknown dtype");
   for (int i = 0; i < n_levels; ++i) {
     const pwc_level_t& L = levels[i];
-    if (S && L.H < kTallMinH) continue;
-    int rc = fwd_entry(L.c1, L.c2, L.flow, L.flow_scale, L.out, B, L.H, L.W, L.C, r, dtype, flow_dtype,
-                       L.out_pixel_stride, main_st);
+    int rc = check_shape(B, L.H, L.W, L.C, r, L.flow != nullptr);
     if (rc) return rc;
+    if ((int64_t)B * L.H * L.W > 0 && (!L.c1 || !L.c2 || !L.out)) return fail(PWC_ERR_BAD_ARG, "level %d: null tensor pointer", i);
+    if (L.out_pixel_stride != 0 && L.out_pixel_stride < (int64_t)(2 * r + 1) * (2 * r + 1))
+      return fail(PWC_ERR_BAD_ARG, "level %d: out_pixel_stride %lld < (2r+1)^2", i, (long long)L.out_pixel_stride);
   }
-  // ... then the short levels side by side (few CTAs each; same H threshold as the kernel choice)
-  if (S) {
-    PWC_CUDA(cudaEventRecord(S->fork, main_st));
-    // largest first: its CTAs take whole SMs (2 x 93 KB); the lighter kernels then fill what is left
-    for (int ii = 0; ii < n_levels; ++ii) {
+  cudaStream_t main_st = (cudaStream_t)cuda_stream;
+  SideStreams* S = (n_levels > 1 && g_overlap.load()) ? side_streams_for_device() : nullptr;
+  int n_side = 0, rc = PWC_OK;
+  bool used[3] = {false, false, false};
+  // The short levels are latency-bound (few CTAs each) and the tall levels' persistent kernels would otherwise own
+  // every SM: the tall kernels leave `side_sms` SMs free, the first of them is launched (its CTAs are placed at once),
+  // then the short levels are forked onto side streams - they can only land on the free SMs and run there NEXT TO
+  // the tall levels instead of after them - and the remaining tall levels follow, in order, on the caller's stream.
+  int n_short = 0;
+  for (int i = 0; i < n_levels; ++i) n_short += (S && levels[i].H < kTallMinH) ? 1 : 0;
+  const int reserve = n_short > 0 && n_short < n_levels ? g_side_sms.load() : 0;
+  if (S && cudaEventRecord(S->fork, main_st) != cudaSuccess) return fail(PWC_ERR_CUDA, "cudaEventRecord failed");
+  bool forked = false;
+  auto fork_short = [&]() {
+    forked = true;
+    // largest first: its CTAs take whole SMs; the lighter kernels then fill what is left
+    for (int ii = 0; ii < n_levels && rc == PWC_OK; ++ii) {
       const int i = g_side_reverse.load() ? n_levels - 1 - ii : ii;
       const pwc_level_t& L = levels[i];
       if (L.H >= kTallMinH) continue;
       const int k = n_side++ % 3;
-      if (!used[k]) { PWC_CUDA(cudaStreamWaitEvent(S->s[k], S->fork, 0)); used[k] = true; }
-      int rc = fwd_entry(L.c1, L.c2, L.flow, L.flow_scale, L.out, B, L.H, L.W, L.C, r, dtype, flow_dtype,
-                         L.out_pixel_stride, S->s[k]);
-      if (rc) return rc;
+      if (!used[k]) {
+        if (cudaStreamWaitEvent(S->s[k], S->fork, 0) != cudaSuccess) { rc = fail(PWC_ERR_CUDA, "cudaStreamWaitEvent failed"); return; }
+        used[k] = true;
+      }
+      rc = fwd_entry(L.c1, L.c2, L.flow, L.flow_scale, L.out, B, L.H, L.W, L.C, r, dtype, flow_dtype,
+                     L.out_pixel_stride, S->s[k]);
     }
+  };
+  for (int i = 0; i < n_levels && rc == PWC_OK; ++i) {
+    const pwc_level_t& L = levels[i];
+    if (S && L.H < kTallMinH) continue;
+    t_reserve_sms = reserve;
+    rc = fwd_entry(L.c1, L.c2, L.flow, L.flow_scale, L.out, B, L.H, L.W, L.C, r, dtype, flow_dtype,
+                   L.out_pixel_stride, main_st);
+    t_reserve_sms = 0;
+    if (S && !forked && rc == PWC_OK) fork_short();
   }
+  if (S && !forked && rc == PWC_OK) fork_short();  // no tall level at all
+  // join whatever was forked, also on the error path: the caller's stream must not be left racing side-stream work
   if (S)
     for (int k = 0; k < 3; ++k)
       if (used[k]) {
-        PWC_CUDA(cudaEventRecord(S->join[k], S->s[k]));
-        PWC_CUDA(cudaStreamWaitEvent(main_st, S->join[k], 0));
+        if (cudaEventRecord(S->join[k], S->s[k]) != cudaSuccess || cudaStreamWaitEvent(main_st, S->join[k], 0) != cudaSuccess)
+          if (rc == PWC_OK) rc = fail(PWC_ERR_CUDA, "joining a side stream failed");
       }
-  return PWC_OK;
+  return rc;
 }
 
 // ---- host-buffer path --------------------------------------------------------------------
@@ -537,6 +641,8 @@ struct pwc_host_ctx {
   std::vector<Buf> bufs;  // 4 per level: c1, c2, flow, out
 };
 
+int pwc_host_ctx_destroy(pwc_host_ctx* c);
+
 int pwc_host_ctx_create(pwc_host_ctx** ctx) {
   if (!ctx) return fail(PWC_ERR_BAD_ARG, "null ctx pointer");
   DevInfo dev;
@@ -544,9 +650,13 @@ int pwc_host_ctx_create(pwc_host_ctx** ctx) {
   if (rc) return rc;
   pwc_host_ctx* c = new (std::nothrow) pwc_host_ctx();
   if (!c) return fail(PWC_ERR_BAD_ARG, "out of host memory");
-  PWC_CUDA(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
-  PWC_CUDA(cudaStreamCreateWithFlags(&c->s_run, cudaStreamNonBlocking));
-  PWC_CUDA(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+  if (cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->s_run, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking) != cudaSuccess) {
+    const cudaError_t e = cudaGetLastError();
+    pwc_host_ctx_destroy(c);  // frees whatever was created
+    return fail(PWC_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+  }
   *ctx = c;
   return PWC_OK;
 }
@@ -617,8 +727,12 @@ int pwc_pyramid_fwd_host(pwc_host_ctx* c, const pwc_level_t* lv, int n_levels, i
     const pwc_level_t& L = lv[i];
     int rc = check_shape(B, L.H, L.W, L.C, r, L.flow != nullptr);
     if (rc) return rc;
+    // the download copies dense rows: a strided host `out` would have its other channels overwritten
+    if (L.out_pixel_stride != 0 && L.out_pixel_stride != D)
+      return fail(PWC_ERR_BAD_ARG, "pwc_pyramid_fwd_host: out_pixel_stride must be 0 (dense host output), got %lld",
+                  (long long)L.out_pixel_stride);
     const size_t npix = (size_t)B * L.H * L.W;
-    const int64_t ops = L.out_pixel_stride ? L.out_pixel_stride : D;
+    const int64_t ops = D;
     if ((rc = ctx_reserve(c, 4 * i + 0, npix * L.C * es))) return rc;
     if ((rc = ctx_reserve(c, 4 * i + 1, npix * L.C * es))) return rc;
     if (L.flow && (rc = ctx_reserve(c, 4 * i + 2, npix * 2 * fs))) return rc;
@@ -642,7 +756,7 @@ int pwc_pyramid_fwd_host(pwc_host_ctx* c, const pwc_level_t* lv, int n_levels, i
       const int lb0 = whole ? 0 : b0, lbn = whole ? B : bn;
       const size_t pix0 = (size_t)lb0 * L.H * L.W, npix = (size_t)lbn * L.H * L.W;
       if (npix == 0) continue;
-      const int64_t ops = L.out_pixel_stride ? L.out_pixel_stride : D;
+      const int64_t ops = D;
       const size_t o_feat = pix0 * L.C * es, nb_feat = npix * L.C * es;
       const size_t o_flow = pix0 * 2 * fs, nb_flow = npix * 2 * fs;
       const size_t o_out = pix0 * ops * es, nb_out = npix * ops * es;
@@ -679,10 +793,15 @@ int pwc_pyramid_fwd_host(pwc_host_ctx* c, const pwc_level_t* lv, int n_levels, i
 
 // ---- backward ------------------------------------------------------------------------------
 size_t pwc_bwd_workspace_bytes(int B, int H, int W, int C, int r, int dtype, int has_flow) {
-  (void)r;
   if (B < 0 || H < 0 || W < 0 || C < 0) return 0;
   // covers both the fused backward and the standalone warp backward (which needs only the fp32 accumulator)
-  return bwd_ws_layout(B, H, W, C, dtype, has_flow != 0).total;
+  size_t need = bwd_ws_layout(B, H, W, C, dtype, has_flow != 0).total;
+  if (r == pwc::bwdf::R && C % pwc::bwdf::KS == 0 && B > 0 && H > 0 && W > 0) {
+    // flow dtype unknown here: assume a 16-bit flow (the larger layout)
+    const size_t f = pwc::bwdf::make_plan(B, H, W, C, elt_size(dtype), 2, has_flow != 0, 148).total;
+    if (f > need) need = f;
+  }
+  return need;
 }
 
 int pwc_cost_volume_bwd(const void* g, const void* out, const void* c1, const void* warp, void* dc1, void* dwarp, int B,

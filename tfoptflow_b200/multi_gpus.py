@@ -73,3 +73,44 @@ def average_gradients(grads, group=None, bucket_bytes: int = 32 << 20):
             flush()
     flush()
     return grads
+
+
+class GradientBucket:
+    """Persistent flat fp32 bucket for the training configuration's one exchange step.
+
+    The reference computes gradients per tower, and in mixed precision un-scales them by the loss scaler and clips
+    them to global norm 5.0 PER TOWER, BEFORE averaging (tfoptflow/model_pwcnet.py:308-315); the towers' gradients are
+    then `tf.reduce_mean`-ed per variable on the controller (`average_gradients`, tfoptflow/multi_gpus.py:68-86).
+    Here: one multi-tensor pack into a bucket allocated once, the same per-rank unscale + clip on the flat view, ONE
+    all-reduce(avg) over NCCL / NVLink (sum + divide on gloo, which has no AVG), one multi-tensor unpack."""
+
+    def __init__(self, grads):
+        live = [g for g in grads if g is not None]
+        if not live:
+            raise ValueError("no gradients")
+        self.sizes = [g.numel() for g in live]
+        self.flat = torch.empty(sum(self.sizes), dtype=torch.float32, device=live[0].device)
+        self.views, off = [], 0
+        for g, n in zip(live, self.sizes):
+            self.views.append(self.flat[off:off + n].view(g.shape))
+            off += n
+
+    def average(self, grads, loss_scale: float | None = None, clip_norm: float | None = None, group=None):
+        live = [g for g in grads if g is not None]  # `if g is not None`, tfoptflow/multi_gpus.py:77
+        if [g.numel() for g in live] != self.sizes:
+            raise ValueError("gradient list does not match the bucket")
+        torch._foreach_copy_(self.views, live)
+        if loss_scale is not None:  # grads / loss_scaler, model_pwcnet.py:313
+            self.flat.mul_(1.0 / float(loss_scale))
+        if clip_norm is not None:  # tf.clip_by_global_norm: t * clip / max(global_norm, clip), model_pwcnet.py:314
+            norm = torch.linalg.vector_norm(self.flat)
+            self.flat.mul_(float(clip_norm) / torch.clamp(norm, min=float(clip_norm)))
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            if dist.get_backend(group) == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+                self.flat.div_(dist.get_world_size(group))
+        torch._foreach_copy_(live, self.views)
+        return grads
+

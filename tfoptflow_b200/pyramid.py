@@ -62,27 +62,44 @@ class PyramidPlan:
         self.tensors = []
         descs = []
         self.outs = []
+        if outs is not None and len(outs) != len(levels):
+            raise ValueError("outs must have one tensor per level")
         for i, L in enumerate(levels):
             c1, c2 = as_cuda_tensor(L["c1"], "c1"), as_cuda_tensor(L["c2"], "c2")
             flow = None if L.get("flow") is None else as_cuda_tensor(L["flow"], "flow")
+            if c1.dim() != 4 or c2.shape != c1.shape or c2.dtype != c1.dtype or c2.device != c1.device:
+                raise ValueError(f"level {i}: c1 and c2 must be [B,H,W,C] tensors of one dtype on one device")
             B, H, W, C = c1.shape
-            out = outs[i] if outs is not None else torch.empty((B, H, W, D), dtype=c1.dtype, device=c1.device)
+            if flow is not None and (tuple(flow.shape) != (B, H, W, 2) or flow.device != c1.device):
+                raise ValueError(f"level {i}: flow must be [B,H,W,2]={[B, H, W, 2]} on the features' device")
+            if outs is not None:
+                out = outs[i]
+                if out.dim() != 4 or tuple(out.shape) != (B, H, W, D) or out.dtype != c1.dtype or out.device != c1.device:
+                    raise ValueError(f"level {i}: out must be a [B,H,W,{D}] view with the feature dtype and device")
+                if out.stride(3) != 1 or out.stride(1) != W * out.stride(2) or out.stride(0) != H * W * out.stride(2):
+                    raise ValueError(f"level {i}: out must be a channel slice of a dense NHWC buffer")
+            else:
+                out = torch.empty((B, H, W, D), dtype=c1.dtype, device=c1.device)
             self.tensors.append((c1, c2, flow))
             self.outs.append(out)
             descs.append(dict(c1=ptr(c1), c2=ptr(c2), flow=ptr(flow), out=ptr(out), H=H, W=W, C=C,
                               flow_scale=float(L.get("scaler", 1.0)), out_pixel_stride=out.stride(2)))
-        self.B = self.tensors[0][0].shape[0]
-        self.device = self.tensors[0][0].device
-        self.dtype = dtype_code(self.tensors[0][0])
+        first = self.tensors[0][0]
+        self.B, self.device, self.dtype = first.shape[0], first.device, dtype_code(first)
         flows = [t[2] for t in self.tensors if t[2] is not None]
         self.flow_dtype = dtype_code(flows[0]) if flows else self.dtype
+        for c1, _, flow in self.tensors:  # one (B, dtype, flow dtype, device) per call: the C entry point takes them once
+            if c1.shape[0] != self.B or dtype_code(c1) != self.dtype or c1.device != self.device or \
+                    (flow is not None and dtype_code(flow) != self.flow_dtype):
+                raise ValueError("all levels of a plan must share batch size, dtypes and device")
         self.arr = _levels_array(descs)
         self.n = len(descs)
         self.lib = _ffi.load()
 
     def run(self):
-        _ffi.check(self.lib.pwc_pyramid_fwd(self.arr, self.n, self.B, self.r, self.dtype, self.flow_dtype,
-                                            stream_ptr(self.device)))
+        with torch.cuda.device(self.device):  # the library launches on the calling thread's current device
+            _ffi.check(self.lib.pwc_pyramid_fwd(self.arr, self.n, self.B, self.r, self.dtype, self.flow_dtype,
+                                                stream_ptr(self.device)))
         return self.outs
 
 
@@ -100,6 +117,9 @@ class HostPyramid:
 
     def run(self, levels, outs, search_range=4):
         descs = []
+        B0, dt0, fdt0 = levels[0]["c1"].shape[0], levels[0]["c1"].dtype, None
+        if dt0 not in self._NP:
+            raise ValueError(f"unsupported feature dtype {dt0} (float32 / float16)")
         for L, o in zip(levels, outs):
             B, H, W, C = L["c1"].shape
             f = L.get("flow")
@@ -107,15 +127,23 @@ class HostPyramid:
                 if arr is not None and not (isinstance(arr, np.ndarray) and arr.flags["C_CONTIGUOUS"]):
                     raise ValueError(f"{name} must be a C-contiguous numpy array (NHWC)")
             if L["c2"].shape != L["c1"].shape or (f is not None and f.shape != (B, H, W, 2)) or \
-                    o.shape != (B, H, W, (2 * int(search_range) + 1) ** 2) or o.dtype != L["c1"].dtype:
-                raise ValueError("c1/c2/flow/out shapes or dtypes do not match")
+                    o.shape != (B, H, W, (2 * int(search_range) + 1) ** 2):
+                raise ValueError("c1/c2/flow/out shapes do not match")
+            if B != B0 or L["c1"].dtype != dt0 or L["c2"].dtype != dt0 or o.dtype != dt0:
+                raise ValueError("every level must share the batch size, and c1/c2/out the feature dtype")
+            if f is not None:
+                if f.dtype not in self._NP:
+                    raise ValueError(f"unsupported flow dtype {f.dtype} (float32 / float16)")
+                if fdt0 is None:
+                    fdt0 = f.dtype
+                elif f.dtype != fdt0:
+                    raise ValueError("all flows of one call must share a dtype")
             descs.append(dict(c1=L["c1"].ctypes.data, c2=L["c2"].ctypes.data, flow=None if f is None else f.ctypes.data,
                               out=o.ctypes.data, H=H, W=W, C=C, flow_scale=float(L.get("scaler", 1.0)),
                               out_pixel_stride=0))
-        dt = self._NP[levels[0]["c1"].dtype]
         arr = _levels_array(descs)
-        _ffi.check(self.lib.pwc_pyramid_fwd_host(self.h, arr, len(descs), levels[0]["c1"].shape[0], int(search_range),
-                                                 dt, dt))
+        _ffi.check(self.lib.pwc_pyramid_fwd_host(self.h, arr, len(descs), B0, int(search_range), self._NP[dt0],
+                                                 self._NP[fdt0 if fdt0 is not None else dt0]))
         return outs
 
     def close(self):
