@@ -56,8 +56,21 @@ const char* pwc_last_error(void);
 /* Number of kernels this library has launched on this process so far (all threads). */
 uint64_t pwc_launch_count(void);
 
-/* Tuning / debug options. Known keys: "fwd_impl" (0 = auto, 1 = generic scalar kernel,
- * 2 = tiled kernel, 3 = streaming kernel). Returns PWC_ERR_BAD_ARG for unknown keys. */
+/* Tuning / debug options (process-wide).  pwc_set_option returns PWC_ERR_BAD_ARG for an unknown key or an out-of-range
+ * value; pwc_get_option reads back every key pwc_set_option accepts.
+ *   "fwd_impl"        0 = auto (default), 1 = generic scalar kernel, 2 = tiled kernel, 3 = streaming kernel
+ *   "bwd_impl"        0 = auto (default: fused K1/K2 kernels for r == 4, C % 32 == 0, dense g / out; else v1),
+ *                     1 = unfused v1 kernels, 2 = fused kernels or PWC_ERR_BAD_ARG when the shape is not covered
+ *   "overlap_levels"  1 (default) = pwc_pyramid_fwd forks the short levels onto side streams, 0 = one stream
+ *   "side_sms"        SMs the tall levels' persistent kernels leave free for those short levels (default 16, 0..64)
+ *   "side_reverse"    1 (default) = fork the short levels largest first
+ *   "tile_small"      1 (default) = 8x16 tiles for levels with fewer 8x32 tiles than SMs
+ *   "bwd_tiled"       1 (default) = register-tiled v1 backward correlation kernels, 0 = one pixel per thread
+ *   "stream_ctas"     CTA count of the streaming kernel (0 = one per SM, default)
+ *   "stream_prefetch" L2 prefetch distance of the streaming kernel in slabs (default 4, 0 = off)
+ *   "stream_debug"    DIAGNOSTICS ONLY, default 0: bits 1 / 2 / 4 skip the correlation / the gathers / the stores
+ *                     of the streaming kernel (RESULTS ARE WRONG; bench.py refuses to report with them set), bit 8
+ *                     forces the LDG path for c1, bit 16 records the event trace read by pwc_debug_read_trace */
 int pwc_set_option(const char* key, int value);
 int pwc_get_option(const char* key, int* value);
 

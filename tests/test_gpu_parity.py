@@ -367,6 +367,48 @@ def test_zero_flow_backward_tie_rule(dev):
     assert_close(g, dflow, 1e-5, "dflow at ties")
 
 
+def test_non_finite_features_do_not_leak_into_the_zero_padding(dev):
+    """The cost volume sees zeros outside the image (core_costvol.py:27) whatever the features hold: a NaN / Inf at
+    c2[b,0,0] (the address the streaming kernel parks out-of-image halo pixels on) must only reach the outputs that
+    really read that pixel, exactly like in the tiled kernel."""
+    d = synth.make_level(2, 40, 52, 32, 601, np.float32, "smooth")
+    d["c2"][0, 0, 0, :] = np.nan
+    d["c2"][1, 0, 0, 3] = np.inf
+    outs = {impl: run_fwd(d, 4, 1.0, dev, impl) for impl in (2, 3)}
+    assert np.array_equal(np.isnan(outs[2]), np.isnan(outs[3]))
+    assert np.array_equal(np.isinf(outs[2]), np.isinf(outs[3]))
+    ok = np.isfinite(outs[2])
+    assert ok.mean() > 0.9
+    assert_close(outs[3][ok], outs[2][ok], 1e-5, "streaming vs tiled with non-finite features")
+
+
+def test_options_round_trip_and_host_path_validation(dev):
+    for key, val in (("fwd_impl", 2), ("bwd_impl", 1), ("overlap_levels", 0), ("side_sms", 8), ("side_reverse", 0),
+                     ("tile_small", 0), ("bwd_tiled", 0), ("stream_ctas", 100), ("stream_prefetch", 2), ("stream_debug", 0)):
+        old = _ffi.get_option(key)
+        _ffi.set_option(key, val)
+        assert _ffi.get_option(key) == val
+        _ffi.set_option(key, old)
+    with pytest.raises(_ffi.PwcError):
+        _ffi.set_option("no_such_option", 1)
+    # host path: fp16 features with an fp32 flow upload the flow with ITS dtype (was: silently read as fp16)
+    lv = synth.make_pyramid(2, 128, 128, np.float16, levels=(3, 2))
+    for L in lv:
+        if L["flow"] is not None:
+            L["flow"] = L["flow"].astype(np.float32)
+    outs = [np.empty(L["c1"].shape[:3] + (81,), np.float16) for L in lv]
+    hp = pyramid.HostPyramid()
+    hp.run(lv, outs, 4)
+    for L, o in zip(lv, outs):
+        ref = O.cost_volume(L["c1"], O.dense_image_warp(L["c2"], L["flow"] * np.float32(L["scaler"])), 4)
+        assert_close(o, ref, 1e-2, f"host path fp16 features / fp32 flow level {L['lvl']}")
+    bad = [dict(L) for L in lv]
+    bad[1]["c2"] = bad[1]["c2"].astype(np.float32)
+    with pytest.raises(ValueError):
+        hp.run(bad, outs, 4)
+    hp.close()
+
+
 def test_out_slice_of_concat_buffer(dev):
     # model_pwcnet.py:1424 concatenates [corr, c1, up_flow, up_feat]; write corr straight into its slice.
     # Second shape: a tall 32-channel level, i.e. the streaming kernel's 6-pixel geometry with a strided output.

@@ -35,44 +35,10 @@ typedef unsigned long long u64;
 constexpr int R = 4, ND = 9, D = 81;
 constexpr int NCW = 8;   // compute warps (two warpgroups)
 constexpr int NPW = 4;   // producer warps (one warpgroup)
-constexpr int NSW_MAX = 4; // store warps (one warpgroup) of the geometries that stage whole tasks
-  // setmaxnreg moves registers inside the CTA allocation: 2*200 + 104 = 3*168
 constexpr int MAXSEG = 8;
 constexpr int GS = 4;    // slabs per task group (one edge task per group)
 constexpr size_t SMEM_LIMIT = 232448;
-#ifndef PWC_STREAM_LD4
-#define PWC_STREAM_LD4 ld4
-#endif
-#ifndef PWC_STREAM_NSLAB8
-#define PWC_STREAM_NSLAB8 12
-#endif
-#ifndef PWC_STREAM_NAP8
-#define PWC_STREAM_NAP8 14
-#endif
-#ifndef PWC_STREAM_GD
-#define PWC_STREAM_GD 3
-#endif
-#ifndef PWC_STREAM_NXG96
-#define PWC_STREAM_NXG96 2
-#endif
-#ifndef PWC_STREAM_NXG128
-#define PWC_STREAM_NXG128 1
-#endif
-#ifndef PWC_STREAM_NSW
-#define PWC_STREAM_NSW 0
-#endif
-#ifndef PWC_STREAM_NSLAB16
-#define PWC_STREAM_NSLAB16 10
-#endif
-#ifndef PWC_STREAM_NAP16
-#define PWC_STREAM_NAP16 14
-#endif
-#ifndef PWC_STREAM_FULLSTAGE
-#define PWC_STREAM_FULLSTAGE 0   /* whole-task staging costs 41 KB that buys more as 4 extra slab slots: 243 -> 225 us */
-#endif
-#ifndef PWC_STREAM_PX32
-#define PWC_STREAM_PX32 6
-#endif
+constexpr int GATHER_DEPTH = 3;   // gather items in flight ahead of the one being blended (3 / 4 / 5 measured equal)
 
 constexpr int pad_to(int v, int r) { return v + ((r - v % 8) + 8) % 8; }  // smallest v' >= v with v' % 8 == r
 constexpr int pad_to16(int v, int r) { return v + ((r - v % 16) + 16) % 16; }
@@ -108,27 +74,20 @@ struct Geo {
   // shuffling ptxas does at every back-edge of a register-starved loop is amortised
   static constexpr int KU = PX <= 6 ? 1 : ((KV / KP) % 8 == 0 ? 8 : ((KV / KP) % 6 == 0 ? 6 : 4));
   // setmaxnreg moves registers inside the CTA allocation (384 x 168): 2 * REGS_COMPUTE + REGS_PRODUCER = 504
-  // Store warps: with whole-task staging (PX <= 6) the compute warps only stage their results; NSW extra warps read
-  // the staged runs back and issue the global stores, so the store latency chain never holds an FFMA2 warp.
-  // (measured on level 2: 289 us with store warps against 241 us without - the scheduler slots they take cost more
-  // than the decoupling gains - so they are off by default; -DPWC_STREAM_NSW=4 turns them on)
-  static constexpr int NCWG = PX <= 4 ? 12 : 8;       // compute warps: 3 per scheduler where 36 accumulator pairs leave room
-  static constexpr int NSW = PX <= 6 ? PWC_STREAM_NSW : 0;
-  static constexpr int NTHREADS = 32 * (NCWG + NPW + NSW);
-  // per-thread budget at launch: 65536 / NTHREADS rounded down to 8 -> 168 (384 threads) or 128 (512 threads)
-  static constexpr int REGS_COMPUTE = PX <= 4 ? 136 : (PX <= 6 ? (NSW ? 184 : 192) : 200);
-  static constexpr int REGS_STORE = 56;
-  static constexpr int REGS_PRODUCER = NCWG == 12 ? 512 - 3 * REGS_COMPUTE : (NSW ? 512 - 2 * REGS_COMPUTE - REGS_STORE : 504 - 2 * REGS_COMPUTE);
-  static_assert(NCWG == 8 || NSW == 0, "thread budget");
+  static constexpr int NCWG = NCW;                    // compute warps (two per scheduler)
+  static constexpr int NTHREADS = 32 * (NCWG + NPW);
+  static constexpr int REGS_COMPUTE = PX <= 6 ? 192 : 200;
+  static constexpr int REGS_PRODUCER = 504 - 2 * REGS_COMPUTE;
   static constexpr int EMPTYB_COUNT = (NXG == 4 ? 2 : 1) + 1;
   static constexpr int LPP = KV >= 8 ? 8 : KV;        // producer lanes per pixel
   static constexpr int KQ = KV / LPP;                 // kv chunks per lane
-  static constexpr int NSLAB = PX <= 4 ? 10 : (KV == 32 && NXG == 2) ? 4 : (KV == 24 && NXG == 2) ? 6 : KV == 32 ? 6 : (KV == 16 ? (PX <= 6 ? PWC_STREAM_NSLAB16 : 6) : (KV == 8 ? PWC_STREAM_NSLAB8 : 7));
-  static constexpr int NAP = PX <= 4 ? 14 : (KV == 32 && NXG == 2) ? 8 : (KV == 24 && NXG == 2) ? 10 : KV == 32 ? 12 : (KV == 8 ? PWC_STREAM_NAP8 : (KV == 16 && PX <= 6 ? PWC_STREAM_NAP16 : 12));     // even: the wrap-around keeps consecutive pairs 2 bank groups apart
-  // transposition buffer per compute warp: all PX pixels at once where shared memory allows (one warp sync per task),
-  // else two pixels, double buffered
-  static constexpr bool FULLSTAGE = PWC_STREAM_FULLSTAGE && PX <= 6 && KV <= 16;
-  static constexpr int STAGE_WORDS = FULLSTAGE ? 320 * PX : 640;
+  // ring lengths (slab slots / c1 pair slots) per geometry: as long as shared memory allows (6 / 8 / 12 slab slots
+  // measured 328 / 243 / 225 us on level 2).  NAP is even: the wrap-around keeps consecutive pairs 2 bank groups apart
+  static constexpr int NSLAB = (KV == 32 && NXG == 2) ? 4 : (KV == 24 && NXG == 2) ? 6 : KV == 32 ? 6 : (KV == 16 ? (PX <= 6 ? 10 : 6) : (KV == 8 ? 12 : 7));
+  static constexpr int NAP = (KV == 32 && NXG == 2) ? 8 : (KV == 24 && NXG == 2) ? 10 : KV == 32 ? 12 : (KV == 8 ? 14 : (KV == 16 && PX <= 6 ? 14 : 12));
+  // transposition buffer per compute warp: two pixels, double buffered (staging the whole task costs 41 KB that buy
+  // more as four extra slab slots)
+  static constexpr int STAGE_WORDS = 640;
   static constexpr size_t OFF_B = 0;
   static constexpr size_t OFF_A = OFF_B + (size_t)NSLAB * BSLOT * 16;
   static constexpr size_t OFF_STAGE = (OFF_A + (size_t)NAP * ASLOT * AB + 15) / 16 * 16;
@@ -137,9 +96,7 @@ struct Geo {
   static constexpr size_t OFF_BAR = OFF_SCRP + (size_t)NPW * NPIX * 8;
   static constexpr size_t OFF_SEG = OFF_BAR + (size_t)(4 * NSLAB + 4 * NAP) * 8;
   static constexpr size_t OFF_ACNT = OFF_SEG + MAXSEG * 32 + 64;                  // consumer arrivals per c1 pair slot
-  static constexpr size_t OFF_DESC = (OFF_ACNT + NAP * 4 + 15) / 16 * 16;            // per compute warp: 32 x {offset, pixels}
-  static constexpr size_t OFF_SBAR = OFF_DESC + (size_t)NCWG * 32 * 16;              // staging full / free barriers
-  static constexpr size_t SMEM_BYTES = OFF_SBAR + 2 * NCWG * 8;
+  static constexpr size_t SMEM_BYTES = (OFF_ACNT + NAP * 4 + 15) / 16 * 16;
   static_assert(SMEM_BYTES <= SMEM_LIMIT, "shared memory budget");
   static_assert(KV % LPP == 0 && KV % KP == 0 && NAP % 2 == 0, "channel split / ring");
   // An edge task waits for the 4 slabs of its group and for the c1 pairs l-5 .. l+3 of those slabs at once: 9 pairs
@@ -198,6 +155,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
+__device__ __forceinline__ int atom_add_acq_rel_cta(int* p, int v) {
+  int old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.s32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+  return old;
+}
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {  // non-blocking
   uint32_t done;
   asm volatile(
@@ -222,13 +184,7 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) 
 
 // ---- packed fp32 (sm_100 FFMA2 / FMUL2) ----------------------------------------------------
 __device__ __forceinline__ void ffma2(u64& d, u64 a, u64 b) {
-#ifdef PWC_STREAM_FFMA2_INTRINSIC
-  float2 dd = *reinterpret_cast<float2*>(&d);
-  dd = __ffma2_rn(*reinterpret_cast<const float2*>(&a), *reinterpret_cast<const float2*>(&b), dd);
-  d = *reinterpret_cast<u64*>(&dd);
-#else
   asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
-#endif
 }
 // scalar weight x packed pair: ptxas folds the {w, w} pair into the scalar-broadcast operand form
 __device__ __forceinline__ void ffma2s(u64& d, float w, u64 b) {
@@ -337,7 +293,7 @@ __device__ __forceinline__ void gather_slab(const T* __restrict__ c2, const Para
   // LPP lanes per pixel, KQ channel chunks per lane
   constexpr int PPI = 32 / G::LPP;               // pixels per warp iteration
   constexpr int NITEMS = G::NPIX * G::KQ / PPI;  // per-lane items of the slab
-  constexpr int GD = HAS_FLOW ? PWC_STREAM_GD : (G::NSW ? 4 : 6);  // items in flight ahead of the one being blended
+  constexpr int GD = HAS_FLOW ? GATHER_DEPTH : 6;  // items in flight ahead of the one being blended
   static_assert((G::NPIX * G::KQ) % PPI == 0 && NITEMS > GD, "gather items");
   constexpr int CELT = G::KV * 4;                // channels (compile-time: corner offsets become immediates)
   constexpr bool HALF = ElemTraits<T>::kIsHalf;
@@ -352,13 +308,13 @@ __device__ __forceinline__ void gather_slab(const T* __restrict__ c2, const Para
       const int r = i % (GD + 1);
       const int e = (i / G::KQ) * PPI + sub, q = i % G::KQ;
       const int2 ps = psc[e];
-      off[r] = ps.y + kvl + q * G::LPP;
+      off[r] = ps.y + kvl + q * G::LPP;   // negative: pixel outside the image (see slab_coords)
       const size_t o = (size_t)ps.x * CELT + 4 * q * G::LPP;
-      tl[r] = PWC_STREAM_LD4(c2k + o);
+      tl[r] = ld4(c2k + o);
       if (HAS_FLOW) {
-        tr[r] = PWC_STREAM_LD4(c2k + o + CELT);
-        bl[r] = PWC_STREAM_LD4(c2k1 + o);
-        br[r] = PWC_STREAM_LD4(c2k1 + o + CELT);
+        tr[r] = ld4(c2k + o + CELT);
+        bl[r] = ld4(c2k1 + o);
+        br[r] = ld4(c2k1 + o + CELT);
       }
     }
     if (i >= GD) {
@@ -377,7 +333,9 @@ __device__ __forceinline__ void gather_slab(const T* __restrict__ c2, const Para
         v = round4<T>(v);
         v.x *= inv_c; v.y *= inv_c; v.z *= inv_c; v.w *= inv_c;
       }
-      sB_slot[off[r]] = v;
+      // outside the image the cost volume sees zeros whatever the features hold: select, do not multiply (0 * NaN)
+      const bool outside = off[r] < 0;
+      sB_slot[off[r] & 0x7fffffff] = outside ? make_float4(0.f, 0.f, 0.f, 0.f) : v;
     }
   }
 }
@@ -433,7 +391,7 @@ __device__ __forceinline__ void slab_coords(const SlabFlow<G, HAS_FLOW, TF>& F, 
         }
       }
       wsc[e] = w;
-      psc[e] = make_int2(pix, bsel * G::BROW + u * G::KV + (u / G::PX) * G::BXPAD);
+      psc[e] = make_int2(pix, (bsel * G::BROW + u * G::KV + (u / G::PX) * G::BXPAD) | (inside ? 0 : (int)0x80000000));
     }
   }
 }
@@ -497,7 +455,7 @@ __device__ __forceinline__ void correlate(const unsigned char* __restrict__ ap, 
 }
 
 template <int KV, int NXG, int PXL, bool HAS_FLOW, bool ATMA, typename T, typename TF>
-__global__ void __launch_bounds__(32 * ((PXL <= 4 ? 12 : 8) + NPW + (PXL <= 6 ? PWC_STREAM_NSW : 0)), 1)
+__global__ void __launch_bounds__(32 * (NCW + NPW), 1)
 fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* __restrict__ flow,
                   T* __restrict__ out, const Params P) {
   using G = Geo<KV, NXG, PXL, ATMA ? (int)sizeof(T) * 4 : 16>;
@@ -515,8 +473,6 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
   Seg* segs = reinterpret_cast<Seg*>(smem + G::OFF_SEG);
   int* s_misc = reinterpret_cast<int*>(smem + G::OFF_SEG + MAXSEG * 32);  // [0] nseg, [1] total tasks, [2] task counter, [3] pairs
   int* a_cnt = reinterpret_cast<int*>(smem + G::OFF_ACNT);
-  int4* sdesc = reinterpret_cast<int4*>(smem + G::OFF_DESC);       // {offset lo, offset hi, pixels in range, kind}
-  uint64_t* sbar = reinterpret_cast<uint64_t*>(smem + G::OFF_SBAR);  // [cw] full, [G::NCWG + cw] free
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int tr_n = 0;
@@ -524,7 +480,6 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
   if (tid == 0) {
     for (int i = 0; i < NBB; ++i) { mbar_init(&fullB[i], 32); mbar_init(&emptyB[i], G::EMPTYB_COUNT); }
     for (int i = 0; i < NBA; ++i) { mbar_init(&fullA[i], ATMA ? 1 : 32); mbar_init(&emptyA[i], 6); }
-    for (int i = 0; i < 2 * G::NCWG; ++i) mbar_init(&sbar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the async (TMA) proxy
     // this CTA's contiguous range of (strip, pair) units, cut into per-strip segments
     const long long qlo = P.Q * blockIdx.x / gridDim.x, qhi = P.Q * (blockIdx.x + 1) / gridDim.x;
@@ -551,63 +506,6 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
   }
   __syncthreads();
   const int nseg = s_misc[0];
-
-  if (G::NSW > 0 && warp >= G::NCWG + NPW) {
-    // =========================== store warps ===========================
-    // Store warp w serves compute warps w and w + NSW: waits for a staged task, reads the 9-channel runs back in store
-    // order (consecutive lanes = consecutive addresses inside a run) and writes them out.
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G::REGS_STORE));
-    const int sw = warp - G::NCWG - NPW;
-    uint32_t par[2] = {0, 0};
-    bool done[2] = {false, false};
-    while (!(done[0] && done[1])) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (done[h]) continue;
-        const int cw = sw + h * G::NSW;
-        if (!mbar_test(&sbar[cw], par[h])) continue;
-        par[h] ^= 1;
-        const int4* dsc = sdesc + cw * 32;
-        if (dsc[0].w != 0) { done[h] = true; continue; }   // the compute warp has left its task loop
-        PWC_TR(12, cw);
-        const float* stage = sStage + cw * G::STAGE_WORDS;
-        T* optr[9];
-        int nv[9];
-        bool all_full = true;
-#pragma unroll
-        for (int it = 0; it < 9; ++it) {
-          const int idx = it * 32 + lane;
-          const int l2 = idx / 9, w = idx - l2 * 9;
-          const int4 dd = dsc[l2];
-          nv[it] = dd.z;
-          optr[it] = out + (((long long)dd.y << 32) | (unsigned)dd.x) + w;
-          all_full = all_full && (dd.z == 0 || dd.z >= G::PX);
-        }
-        all_full = __all_sync(0xffffffffu, all_full);
-        if (!(P.dbg & 4)) {
-#pragma unroll
-          for (int p = 0; p < G::PX; ++p) {
-            float v[9];
-#pragma unroll
-            for (int it = 0; it < 9; ++it) v[it] = stage[p * 320 + it * 32 + lane];
-            if (all_full) {
-#pragma unroll
-              for (int it = 0; it < 9; ++it)
-                if (nv[it] > 0) optr[it][(size_t)p * P.ops] = ElemTraits<T>::from_f(v[it]);
-            } else {
-#pragma unroll
-              for (int it = 0; it < 9; ++it)
-                if (p < nv[it]) optr[it][(size_t)p * P.ops] = ElemTraits<T>::from_f(v[it]);
-            }
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sbar[G::NCWG + cw]);  // staging buffer and descriptor are free again
-        PWC_TR(13, cw);
-      }
-    }
-    return;
-  }
 
   if (warp >= G::NCWG) {
     // =========================== producers ===========================
@@ -674,7 +572,6 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
   float* stage = sStage + warp * G::STAGE_WORDS;
   const int total_tasks = s_misc[1];
   const int lo = lane & 1;
-  uint32_t spar = 0;  // phase of this warp's staging-free barrier
   while (true) {
     int t = 0;
     if (lane == 0) t = atomicAdd(&s_misc[2], 1);
@@ -742,9 +639,10 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
     if (slab_ok && arrive_b) mbar_arrive(&emptyB[jg % NBB]);
     if (pair_ok && arrive_a) {
       if constexpr (ATMA) {
-        // no fence: every shared-memory read of this slot has already delivered its value (the FFMA2s consumed it, and
-        // __syncwarp above covers the other lanes); a MEMBAR here would also wait for the previous task's global stores
-        if (atomicAdd(&a_cnt[sa], 1) == 5) {  // last of the 6 arrivals: the slot is free, refill it with pair ag + NAP
+        // The arrival is an acq_rel atomic at CTA scope: the other warps' reads of the slot (their arrivals release them)
+        // happen-before the refilling lane's fence.proxy.async + TMA overwrite.  CTA scope orders shared-memory accesses
+        // only; it does not wait for the previous task's global stores.
+        if (atom_add_acq_rel_cta(&a_cnt[sa], 1) == 5) {  // last of the 6 arrivals: the slot is free, refill it with pair ag + NAP
           a_cnt[sa] = 0;
           if (ag + G::NAP < s_misc[3]) refill_pair_tma<G, T>(c1, P, segs, nseg, ag + G::NAP, sA, fullA);
           if ((P.dbg & 16) && blockIdx.x == 0 && lane == 0 && tr_n < TRACE_LEN) g_trace[warp][tr_n++] = ((unsigned long long)clock64() << 16) | (13 << 12) | (lane & 0xfff);
@@ -778,18 +676,7 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
         stg[lane * 9 + d] = fmaxf(0.1f * v, v);
       }
     };
-    if constexpr (G::FULLSTAGE && G::NSW > 0) {
-      // hand the task to the store warp: wait until it has drained this warp's previous task, publish where the
-      // runs go, stage all pixels, signal
-      mbar_wait(&sbar[G::NCWG + warp], spar ^ 1);
-      spar ^= 1;
-      sdesc[warp * 32 + lane] = make_int4((int)(unsigned)(my_off & 0xffffffffll), (int)(my_off >> 32), my_nv, 0);
-#pragma unroll
-      for (int p = 0; p < G::PX; ++p) stage_pixel(p, stage + p * 320);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sbar[warp]);
-    } else if constexpr (G::FULLSTAGE) {
-      // every pixel is staged, then one warp sync, then all stores: no serial stage -> sync -> store chain per pixel
+    {
       T* optr[9];
       int nv[9];
 #pragma unroll
@@ -800,40 +687,6 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
         nv[it] = __shfl_sync(0xffffffffu, my_nv, l2);
         optr[it] = out + o + w;
       }
-#pragma unroll
-      for (int p = 0; p < G::PX; ++p) stage_pixel(p, stage + p * 320);
-      __syncwarp();
-      // nv == 0 marks a lane without output; with all_full every other lane has all PX pixels inside the image
-      const bool all_full = __all_sync(0xffffffffu, my_nv >= G::PX || !writer);
-      if (!(P.dbg & 4)) {
-#pragma unroll
-        for (int p = 0; p < G::PX; ++p) {
-          float v[9];
-#pragma unroll
-          for (int it = 0; it < 9; ++it) v[it] = stage[p * 320 + it * 32 + lane];  // unconditional: the buffer is ours
-          if (all_full) {
-#pragma unroll
-            for (int it = 0; it < 9; ++it)
-              if (nv[it] > 0) optr[it][(size_t)p * P.ops] = ElemTraits<T>::from_f(v[it]);
-          } else {
-#pragma unroll
-            for (int it = 0; it < 9; ++it)
-              if (p < nv[it]) optr[it][(size_t)p * P.ops] = ElemTraits<T>::from_f(v[it]);
-          }
-        }
-      }
-      __syncwarp();
-    } else {
-      T* optr[9];
-      int nv[9];
-#pragma unroll
-    for (int it = 0; it < 9; ++it) {
-      const int idx = it * 32 + lane;
-      const int l2 = idx / 9, w = idx - l2 * 9;
-      const long long o = __shfl_sync(0xffffffffu, my_off, l2);
-      nv[it] = __shfl_sync(0xffffffffu, my_nv, l2);
-      optr[it] = out + o + w;
-    }
       // software pipeline over the pixels: pixel p + 1 is staged while pixel p is read back and stored
       stage_pixel(0, stage);
       __syncwarp();
@@ -848,12 +701,6 @@ fwd_stream_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* 
       }
     }
     PWC_TR(11, t);
-  }
-  if constexpr (G::FULLSTAGE && G::NSW > 0) {  // tell the store warp that this compute warp is done
-    mbar_wait(&sbar[G::NCWG + warp], spar ^ 1);
-    sdesc[warp * 32 + lane] = make_int4(0, 0, 0, 1);
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&sbar[warp]);
   }
 }
 
@@ -902,10 +749,10 @@ int launch(const T* c1, const T* c2, const TF* flow, float flow_scale, T* out, i
   return launch_cfg<KV, NXG, PXL, T, TF>(c1, c2, flow, flow_scale, out, B, H, W, C, ops, st, sms, ctas_override, pf_dist, dbg)
   switch (C) {
     case 16: PWC_STREAM_GO(4, 4, 6);
-    case 32: PWC_STREAM_GO(8, 4, PWC_STREAM_PX32);
+    case 32: PWC_STREAM_GO(8, 4, 6);
     case 64: PWC_STREAM_GO(16, 2, 6);
-    case 96: PWC_STREAM_GO(24, PWC_STREAM_NXG96, 6);
-    case 128: PWC_STREAM_GO(32, PWC_STREAM_NXG128, 6);
+    case 96: PWC_STREAM_GO(24, 2, 6);
+    case 128: PWC_STREAM_GO(32, 1, 6);
     default: return 1;
   }
 #undef PWC_STREAM_GO

@@ -15,6 +15,8 @@ namespace tile {
 
 // TW x PX: 32 x 4 (256-pixel tiles, 2 CTAs per SM) for levels with enough tiles to fill the GPU; 16 x 2 (128-pixel tiles,
 // 48 KB, 3 CTAs per SM) for the short pyramid levels, which are latency-bound and want more, lighter CTAs.
+// search_range 8 (BASELINE configs[4], 289 channels): 16 x 2 with 17 warps (one dy each, 68 accumulators per thread,
+// 112 registers), 148 KB of output staging, one CTA per SM; that workload is FMA-bound.
 template <int R_, int TW_ = 32, int PX_ = 4>
 struct Cfg {
   static constexpr int R = R_;
@@ -44,7 +46,7 @@ template <int R, int TWC, int PXC, typename T, typename TF>
 #ifndef PWC_TILE_MAXNREG
 #define PWC_TILE_MAXNREG 96   /* 2 CTAs/SM (9 warps x 96 regs x 2); measured faster than 112 regs x 1 CTA */
 #endif
-__global__ void __maxnreg__(TWC == 32 ? PWC_TILE_MAXNREG : 72)
+__global__ void __maxnreg__(R == 8 ? 112 : (TWC == 32 ? PWC_TILE_MAXNREG : 72))
 fwd_tile_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* __restrict__ flow,
                 float flow_scale, T* __restrict__ out, int B, int H, int W, int C,
                 int64_t out_pixel_stride, int tiles_x, int tiles_y) {
@@ -95,7 +97,7 @@ fwd_tile_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* __
     __syncthreads();  // coords visible / previous chunk consumed
     // ---- phase 1a: c1 tile (FA loads in flight per thread) ----
     {
-      constexpr int NA = TH * TW * KV, FA = 4;
+      constexpr int NA = TH * TW * KV, FA = R == 8 ? 2 : 4;
 #pragma unroll 1
       for (int i0 = tid; i0 < NA; i0 += FA * K::NTHREADS) {
         float4 v[FA];
@@ -119,7 +121,7 @@ fwd_tile_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* __
     }
     // ---- phase 1b: warped c2 tile + halo (FB items = 4*FB corner loads in flight per thread) ----
     {
-      constexpr int NB = K::COORD_N * KV, FB = 3;
+      constexpr int NB = K::COORD_N * KV, FB = R == 8 ? 1 : 3;  // r = 8: 68 accumulators leave room for one item
       const size_t rowstride = (size_t)W * C;
 #pragma unroll 1
       for (int i0 = tid; i0 < NB; i0 += FB * K::NTHREADS) {

@@ -121,10 +121,11 @@ int fwd_typed(const void* c1, const void* c2, const void* flow, float flow_scale
   const size_t va = sizeof(T) * 4;  // vector alignment for 4-element loads
   const bool vec_ok = (C % 4 == 0) && aligned(c1, va) && aligned(c2, va);
   int impl = g_fwd_impl.load();
-  const bool tuned_ok = r == 4 && vec_ok;
+  const bool tuned_ok = (r == 4 || r == 8) && vec_ok;
   // auto: the streaming kernel wins on tall levels (it pays ~5 warm-up slabs per strip segment), the tiled kernel
   // on short ones; measured crossover between H = 28 and H = 56 (profiles/r01_notes.md)
-  if (impl == 0) impl = !tuned_ok ? 1 : (H >= kTallMinH ? 3 : 2);
+  if (impl == 0) impl = !tuned_ok ? 1 : (r == 4 && H >= kTallMinH ? 3 : 2);
+  if (impl == 3 && r != 4) impl = 2;  // the streaming kernel is written for search_range 4
   // un-warped small level (the pyramid top): too few tiles for the tiled kernel, one thread per output element wins
   if (g_fwd_impl.load() == 0 && flow == nullptr && vec_ok && (int64_t)B * H * W <= 16384) {
     if (r == 4 && W % 2 == 0) {
@@ -162,7 +163,7 @@ int fwd_typed(const void* c1, const void* c2, const void* flow, float flow_scale
   if (impl == 2) {
     auto launch_tile = [&](auto cfg, auto kern, int slot) -> int {
       using K = decltype(cfg);
-      static std::atomic<uint64_t> attr_set[2];  // per (T,TF) instantiation and tile shape; one bit per device
+      static std::atomic<uint64_t> attr_set[3];  // per (T,TF) instantiation and tile shape; one bit per device
       int devid = 0;
       PWC_CUDA(cudaGetDevice(&devid));
       if (!((attr_set[slot].load() >> devid) & 1)) {
@@ -186,6 +187,7 @@ int fwd_typed(const void* c1, const void* c2, const void* flow, float flow_scale
     };
     // short levels: fewer full-size tiles than SMs -> the small tile shape (more, lighter CTAs; measured: level 5
     // 76 -> 46 us, while level 4 with 256 full-size tiles is faster as it is: 91 vs 119 us)
+    if (r == 8) return launch_tile(pwc::tile::Cfg<8, 16, 2>(), pwc::tile::fwd_tile_kernel<8, 16, 2, T, TF>, 2);
     const int64_t big_tiles = (int64_t)((W + 31) / 32) * ((H + 7) / 8) * B;
     if (big_tiles < (int64_t)dev.sms && g_tile_small.load())
       return launch_tile(pwc::tile::Cfg<4, 16, 2>(), pwc::tile::fwd_tile_kernel<4, 16, 2, T, TF>, 1);
