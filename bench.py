@@ -12,6 +12,8 @@ Sintel 436x1024 padded to 448x1024, batch 32 per GPU, search_range 4, fp32, forw
   --config 2 (default)  448x1024, batch 32, r=4, forward (fp32 unless --dtype fp16)       BASELINE configs[2]
   --config 0            384x512, batch 1, r=4, fp32 forward                                BASELINE configs[0] (operator part)
   --config 1            384x512, batch 8, six levels all warped, fp32 forward + backward   BASELINE configs[1]
+  --config 3            pwcnet-sm-6-2 training step, 384x448 crops, batch 8 per GPU, mixed precision, data-parallel
+                        with one NCCL all-reduce of the gradients (needs the PyTorch PWC-Net of model_pwcnet.py)  configs[3]
   --config 4            1088x1920, batch 16, r=8 (289 channels), fp16 forward              BASELINE configs[4]
   --mode allreduce      the training configuration's one exchange step (multi_gpus.average_gradients over NCCL)
 
@@ -44,6 +46,7 @@ PRESETS = {
     0: dict(height=384, width=512, batch=1, search_range=4, dtype="fp32", mode="fwd", levels=(6, 5, 4, 3, 2), top_flow=False),
     1: dict(height=384, width=512, batch=8, search_range=4, dtype="fp32", mode="fwdbwd", levels=(6, 5, 4, 3, 2, 1), top_flow=True),
     2: dict(height=448, width=1024, batch=32, search_range=4, dtype="fp32", mode="fwd", levels=(6, 5, 4, 3, 2), top_flow=False),
+    3: dict(height=384, width=448, batch=8, search_range=4, dtype="fp16", mode="train", levels=(6, 5, 4, 3, 2), top_flow=False),
     4: dict(height=1088, width=1920, batch=16, search_range=8, dtype="fp16", mode="fwd", levels=(6, 5, 4, 3, 2), top_flow=False),
 }
 OPTION_DEFAULTS = {"fwd_impl": 0, "bwd_impl": 0, "stream_ctas": 0, "stream_prefetch": 4, "stream_debug": 0,
@@ -57,7 +60,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=sorted(PRESETS))
-    ap.add_argument("--mode", default=None, choices=["fwd", "fwdbwd", "allreduce"])
+    ap.add_argument("--mode", default=None, choices=["fwd", "fwdbwd", "allreduce", "train"])
     ap.add_argument("--dtype", default=None, choices=["fp32", "fp16"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --batch pairs on every GPU; strong: --batch pairs in total, batch/N per GPU (configs[2])")
@@ -224,7 +227,7 @@ def run_reference(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return 0
-    if a.mode == "allreduce":
+    if a.mode in ("allreduce", "train"):
         print(json.dumps({"impl": "reference", "unavailable": "the reference's gradient averaging is a TF graph op on the "
                           "controller device (multi_gpus.py:68-86); there is no CPU-runnable collective to time"}), flush=True)
         return 0
@@ -305,6 +308,8 @@ def run_ours(a):
     dev = torch.device("cuda", local)
     if a.mode == "allreduce":
         return run_allreduce(a, rank, world, local, dev)
+    if a.mode == "train":
+        return run_train(a, rank, world, local, dev)
     _ffi.load()
     if a.fwd_impl:
         _ffi.set_option("fwd_impl", a.fwd_impl)
@@ -473,6 +478,7 @@ def run_ours(a):
         def pinned(arr):
             return torch.from_numpy(arr).pin_memory()
         n_e2e = a.e2e_steps or min(a.steps, 20)
+        ceiling = None
         if not bwd:  # pwc_pyramid_fwd_host: H2D, kernels and D2H overlapped on three streams
             keep, hl, houts = [], [], []
             for d in host_levels:
@@ -498,6 +504,34 @@ def run_ours(a):
             t_e2e = (time.perf_counter() - t0) / n_e2e
             path = "pwc_pyramid_fwd_host: pinned host buffers -> H2D -> kernels -> D2H, 3 streams"
             hp.close()
+            # ceiling of this path: the same bytes as bare copies (uploads on one stream, downloads on another, all
+            # ranks at once, no kernels) - what the host link gives N concurrent processes on this box
+            s_up, s_dn = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            ups = [(L[k], torch.from_numpy(e[k])) for L, e in zip(dev_levels, hl) for k in ("c1", "c2", "flow") if e[k] is not None]
+            devouts = [o for p_ in plans for o in p_.outs]  # level shapes are distinct: pair host / device outputs by shape
+            dns = [(torch.from_numpy(o), next(d_ for d_ in devouts if tuple(d_.shape) == o.shape)) for o in houts]
+
+            def bare():
+                with torch.cuda.stream(s_up):
+                    for dst, src in ups:
+                        dst.copy_(src, non_blocking=True)
+                with torch.cuda.stream(s_dn):
+                    for dst, src in dns:
+                        dst.copy_(src, non_blocking=True)
+                s_up.synchronize()
+                s_dn.synchronize()
+            bare()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                bare()
+            t_bare = (time.perf_counter() - t0) / 3
+            if world > 1:
+                t = torch.tensor([t_bare], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                t_bare = float(t[0])
+            ceiling = {"bare_copy_ms": t_bare * 1e3, "per_gpu_gbs": (h2d + d2h) / t_bare / 1e9,
+                       "aggregate_gbs": world * (h2d + d2h) / t_bare / 1e9}
         else:  # training-shaped call: inputs and upstream gradients up, gradients down, through the C ABI
             hin = [{k: (None if d[k] is None else pinned(d[k])) for k in ("c1", "c2", "flow", "g")} for d in host_levels]
             hgr = [tuple(None if t is None else torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in k[:3])
@@ -532,6 +566,9 @@ def run_ours(a):
         e2e = {"value": pairs_step / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "steps": n_e2e, "ms_per_step": t_e2e * 1e3, "path": path,
                "host_link_gbs": (h2d + d2h) / t_e2e / 1e9}
+        if ceiling is not None:  # the roofline of the end-to-end path is the host link, not HBM
+            e2e["host_link_ceiling"] = ceiling
+            e2e["frac_of_host_link_ceiling"] = ceiling["bare_copy_ms"] / (t_e2e * 1e3)
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -558,6 +595,94 @@ def run_ours(a):
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_train(a, rank, world, local, dev):
+    """BASELINE configs[3]: one training step of pwcnet-sm-6-2 per iteration - forward (cuDNN convolutions + this
+    library's fused warp + cost volume at every level), pwcnet_loss, backward (this library's fused backward), the
+    reference's per-rank unscale 1/128 + clip 5.0, ONE NCCL all-reduce(avg) of the flat gradient bucket, Adam
+    (model_pwcnet.py:254-339).  Mixed precision = fp16 activations under autocast with fp32 master weights
+    (mixed_precision.py:23-37).  Random-init weights, synthetic image pairs and flows."""
+    import torch
+    import torch.distributed as dist
+    from tfoptflow_b200 import _ffi, model_pwcnet as M, multi_gpus
+    _ffi.load()
+    mixed = a.dtype == "fp16"
+    opts = M.pwcnet_options(a.params, use_mixed_precision=mixed)
+    torch.manual_seed(1969)
+    model = M.ModelPWCNet(opts).to(dev).to(memory_format=torch.channels_last)
+    optim = torch.optim.Adam(model.parameters(), lr=1e-4, eps=1e-4 if mixed else 1e-8)  # model_pwcnet.py:266-270
+    params = [p for p in model.parameters()]
+    g = torch.Generator(device=dev).manual_seed(1969 + rank)
+    x = torch.rand((a.batch, 2, a.height, a.width, 3), device=dev, generator=g)
+    y = torch.randn((a.batch, a.height, a.width, 2), device=dev, generator=g) * 4.0
+    xh, yh = x.cpu().pin_memory(), y.cpu().pin_memory()
+    bucket = None
+    scale = float(opts["loss_scaler"]) if mixed else None
+
+    def step(from_host=False):
+        nonlocal bucket
+        if from_host:
+            x.copy_(xh, non_blocking=True)
+            y.copy_(yh, non_blocking=True)
+        optim.zero_grad(set_to_none=False)
+        with torch.autocast("cuda", dtype=torch.float16, enabled=mixed):
+            flow_pred, flow_pyr = model(x)
+        loss = M.pwcnet_loss(y, flow_pyr, opts) + M.l2_regulariser(model, opts["gamma"])
+        (loss * scale if mixed else loss).backward()
+        grads = [p.grad for p in params]
+        if bucket is None:
+            bucket = multi_gpus.GradientBucket(grads)
+        bucket.average(grads, loss_scale=scale, clip_norm=5.0 if mixed else None)
+        optim.step()
+        return loss
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    torch.cuda.synchronize(dev)
+    launches0 = _ffi.launch_count()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with sampler:
+        e0.record()
+        for _ in range(a.steps):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / a.steps
+    launches = _ffi.launch_count() - launches0
+    n_e2e = a.e2e_steps or min(a.steps, 10)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        lv = float(step(from_host=True))  # reads the loss back: D2H inside the timed region
+    t_e2e = (time.perf_counter() - t0) / n_e2e
+    if world > 1:
+        t = torch.tensor([ms, t_e2e * 1e3], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, t_e2e = float(t[0]), float(t[1]) / 1e3
+    if rank == 0:
+        print(json.dumps({
+            "metric": "training samples/sec, pwcnet-%s-6-2 (image pairs per second)" % a.params, "value": world * a.batch / (ms / 1e3),
+            "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16" if mixed else "f32",
+            "data": "synthetic",
+            "config": {"workload": f"BASELINE.json configs[3]: pwcnet-{a.params}-6-2 training step, {a.height}x{a.width}, batch "
+                                   f"{a.batch}/GPU, {'mixed precision (fp16 autocast, fp32 master weights, loss scale 128, clip 5.0)' if mixed else 'fp32'}, "
+                                   f"data-parallel, one NCCL all-reduce(avg) of {sum(p.numel() for p in params)} fp32 gradients, Adam",
+                       "pairs_per_step": world * a.batch},
+            "published_context": "reference trains sm at 52.3 -> 38.1 samples/s on Titan X + 1080 Ti (2 x 16, 256x448, fp32; "
+                                 "pwcnet_train_sm-6-2-cyclic-chairsthingsmix.ipynb:299,1015) - other hardware and crop, not comparable",
+            "final_loss": lv, "clocks": sampler.summary(), "gpu_launches": int(launches),
+            "e2e": {"value": world * a.batch / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(xh.numel() * 4 + yh.numel() * 4),
+                    "d2h_bytes_per_step": 4, "steps": n_e2e, "ms_per_step": t_e2e * 1e3,
+                    "path": "pinned host batch -> H2D -> training step -> loss read back"}}), flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0

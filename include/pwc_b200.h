@@ -58,7 +58,8 @@ uint64_t pwc_launch_count(void);
 
 /* Tuning / debug options (process-wide).  pwc_set_option returns PWC_ERR_BAD_ARG for an unknown key or an out-of-range
  * value; pwc_get_option reads back every key pwc_set_option accepts.
- *   "fwd_impl"        0 = auto (default), 1 = generic scalar kernel, 2 = tiled kernel, 3 = streaming kernel
+ *   "fwd_impl"        0 = auto (default), 1 = generic scalar kernel, 2 = tiled kernel, 3 = streaming kernel,
+ *                     4 = tensor-core band GEMM for 16-bit features (r == 4, C in {32, 64}; other shapes fall back)
  *   "bwd_impl"        0 = auto (default: fused K1/K2 kernels for r == 4, C % 32 == 0, dense g / out; else v1),
  *                     1 = unfused v1 kernels, 2 = fused kernels or PWC_ERR_BAD_ARG when the shape is not covered
  *   "overlap_levels"  1 (default) = pwc_pyramid_fwd forks the short levels onto side streams, 0 = one stream

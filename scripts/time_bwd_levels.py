@@ -15,7 +15,7 @@ lib = _ffi.load()
 dev = torch.device("cuda", 0)
 peak = 6553.0
 tot = {}
-for impl in (1, 0):
+for impl in ((0,) if os.environ.get("PWC_BWD_ONLY_FUSED") else (1, 0)):
     _ffi.set_option("bwd_impl", impl)
     for k, v in opts:
         _ffi.set_option(k, int(v))

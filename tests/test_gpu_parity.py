@@ -113,10 +113,13 @@ def test_golden_backward(path, bwd_impl, dev):
     out.backward(to_dev(z["g"], dev))
     torch.cuda.synchronize()
     name = os.path.basename(path)[:-4]
-    assert_close(c1.grad.cpu().numpy(), z["dc1"], 1e-5, f"{name} dc1 (bwd_impl {bwd_impl})")
-    assert_close(c2.grad.cpu().numpy(), z["dc2"], 1e-5, f"{name} dc2 (bwd_impl {bwd_impl})")
+    # floor 1.0: the fixtures are exact (float64) gradients, while any fp32 evaluation - TensorFlow's included - rounds
+    # the sampling coordinate j - flow * scale to fp32 first (4e-6 px at x = 50), which moves the warped features by
+    # that much; against the fp32-faithful oracle the same kernels sit at ~1e-6 x rms (the other backward tests)
+    assert_close(c1.grad.cpu().numpy(), z["dc1"], 1e-5, f"{name} dc1 (bwd_impl {bwd_impl})", floor=1.0)
+    assert_close(c2.grad.cpu().numpy(), z["dc2"], 1e-5, f"{name} dc2 (bwd_impl {bwd_impl})", floor=1.0)
     if flow is not None:
-        assert_close(flow.grad.cpu().numpy(), z["dflow"], 1e-5, f"{name} dflow (bwd_impl {bwd_impl})")
+        assert_close(flow.grad.cpu().numpy(), z["dflow"], 1e-5, f"{name} dflow (bwd_impl {bwd_impl})", floor=1.0)
 
 
 def _bwd_case(dev, b, h, w, c, seed, dtype=np.float32, flow="smooth", fs=2.5, flow_dtype=None, tol=1e-5, what=""):

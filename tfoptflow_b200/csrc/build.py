@@ -10,7 +10,7 @@ PKG = os.path.dirname(HERE)
 LIB_DIR = os.path.join(PKG, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libpwc_b200.so")
 SOURCES = ["pwc_abi.cu"]
-HEADERS = ["common.cuh", "fwd_generic.cuh", "fwd_tile.cuh", "fwd_stream.cuh", "bwd.cuh", "bwd_fused.cuh",
+HEADERS = ["common.cuh", "fwd_generic.cuh", "fwd_tile.cuh", "fwd_stream.cuh", "bwd.cuh", "bwd_fused.cuh", "fwd_mma16.cuh",
            os.path.join("..", "..", "include", "pwc_b200.h")]
 
 

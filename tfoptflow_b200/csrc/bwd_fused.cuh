@@ -18,6 +18,10 @@
 //     the two halves, the A operand is a scalar-broadcast FFMA2 source shared by the 4 channel groups of a pixel group.
 //   * K2 hands finished dwarp rows to 4 scatter warps (red.global.add.v4.f32 into an fp32 dc2, warp-shuffle dflow).
 // Synchronisation: mbarriers only (full per ring slot, done per task); no __syncthreads after the role split.
+// A parity wait also passes when the barrier is one whole phase BEHIND the one waited for (the parity then names the
+// preceding phase), so every barrier here has either a single producer and a single consumer that alternate strictly
+// (staging slots), or two alternating barrier sets per data slot (rings: index i % 2N, parity (i / 2N) & 1), or a
+// dependency chain that keeps waiters less than one lap ahead (task-done barriers, see wait_window_free).
 #pragma once
 #include "common.cuh"
 
@@ -37,7 +41,7 @@ constexpr int SROW = TW * 8 + TW / 8;       // float4 per staged dwarp row (same
 constexpr int NW = 18;                      // window ring slots: 4 tasks in flight span 16 rows, + 2 ahead
 constexpr int NG = 10;                      // A ring slots: 4 tasks x 2 rows in flight, + 2 ahead
 constexpr int NT = 16;                      // task-done barriers
-constexpr int NDS = 4;                      // staged dwarp rows (one per scatter warp)
+constexpr int NDS = 8;                      // staged dwarp rows: two (one per half) per consumer warp, drained by its own scatter warp
 constexpr int NCW = 4, NAW = 4;             // consumer / A-producer warps
 constexpr int NTHREADS = 512;
 constexpr int REGS_CONSUMER = 200, REGS_OTHER = 104;   // 128 * 200 + 384 * 104 = 512 * 128
@@ -47,7 +51,7 @@ constexpr size_t OFF_A = OFF_W + (size_t)NW * WROW * 16;
 constexpr size_t OFF_Z = OFF_A + (size_t)NG * AROW * 16;
 constexpr size_t OFF_S = OFF_Z + (size_t)ASLICE * 16;
 constexpr size_t OFF_BAR = OFF_S + (size_t)NDS * SROW * 16;
-constexpr int NBAR = NW + NG + NT + 2 * NDS;
+constexpr int NBAR = 2 * NW + 2 * NG + NT + 2 * NDS;
 constexpr size_t SMEM_BYTES = OFF_BAR + (size_t)NBAR * 8;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
@@ -242,7 +246,7 @@ __device__ __forceinline__ void produce_window(const Args& a, const Unit& un, fl
         }
       }
     }
-    mbar_arrive(&full_w[u % NW]);
+    mbar_arrive(&full_w[u % (2 * NW)]);
   }
 }
 
@@ -305,7 +309,7 @@ __device__ __forceinline__ void produce_a_k1(const Args& a, const Unit& un, floa
       }
       __syncwarp();
     }
-    mbar_arrive(&full_a[j % NG]);
+    mbar_arrive(&full_a[j % (2 * NG)]);
   }
 }
 
@@ -347,7 +351,7 @@ __device__ __forceinline__ void produce_a_k2(const Args& a, const Unit& un, floa
           for (int ex = 0; ex < ND; ++ex) A[a_index(lane, (ey0 + q) * ND + ex, ex)] = v[q][ex];
       }
     }
-    mbar_arrive(&full_a[j % NG]);
+    mbar_arrive(&full_a[j % (2 * NG)]);
   }
 }
 
@@ -361,8 +365,8 @@ __device__ __forceinline__ void consume(const Args& a, const Unit& un, const flo
   const int h = lane >> 4, s = lane & 15, pg = s >> 2, cg = s & 3;
   const int g0 = 2 * pg, g1 = 2 * pg + 1;
   for (int p = warp; p < un.P; p += NCW) {
-    mbar_wait(&full_a[(2 * p) % NG], ((2 * p) / NG) & 1);
-    mbar_wait(&full_a[(2 * p + 1) % NG], ((2 * p + 1) / NG) & 1);
+    mbar_wait(&full_a[(2 * p) % (2 * NG)], ((2 * p) / (2 * NG)) & 1);
+    mbar_wait(&full_a[(2 * p + 1) % (2 * NG)], ((2 * p + 1) / (2 * NG)) & 1);
     const float4* Abase = sA + (size_t)((2 * p + h) % NG) * AROW;
     u64 acc[8][4];
 #pragma unroll
@@ -373,7 +377,7 @@ __device__ __forceinline__ void consume(const Args& a, const Unit& un, const flo
 #pragma unroll 1
     for (int t = 0; t < ND + 1; ++t) {
       const int u = 2 * p + t;
-      mbar_wait(&full_w[u % NW], (u / NW) & 1);
+      mbar_wait(&full_w[u % (2 * NW)], (u / (2 * NW)) & 1);
       const ulonglong2* Wr = reinterpret_cast<const ulonglong2*>(sW + (size_t)(u % NW) * WROW + pg * 65 + 2 * cg);
       const int ey = t - h;  // the two halves use the same window row for different displacements
       const float4* Ar = (ey >= 0 && ey < ND) ? Abase + ey * ASLICE : sZ;
@@ -401,7 +405,8 @@ __device__ __forceinline__ void consume(const Args& a, const Unit& un, const flo
     const int j = 2 * p + h;
     const bool rowv = j < un.rows;
     if (MODE == 1 && HAS_FLOW) {
-      const int slot = j % NDS, k = j / NDS;
+      // this warp's own two staging slots (one per half), drained by scatter warp `warp`: one producer, one consumer
+      const int slot = 2 * warp + h, k = p / NCW;
       if (rowv) {
         if (k > 0) mbar_wait(&empty_d[slot], (k - 1) & 1);
         float4* S = sS + (size_t)slot * SROW + pg * 65 + 2 * cg;
@@ -438,9 +443,14 @@ __device__ __forceinline__ void scatter_rows(const Args& a, const Unit& un, cons
   const T* __restrict__ c2 = reinterpret_cast<const T*>(a.c2);
   const TF* __restrict__ flow = reinterpret_cast<const TF*>(a.flow);
   const int psub = lane >> 3, f4 = lane & 7;
-  for (int j = sw; j < un.rows; j += NDS) {
-    mbar_wait(&full_d[sw], (j / NDS) & 1);
-    const float4* S = sS + (size_t)sw * SROW;
+  // rows 2p, 2p+1 of the tasks p = sw, sw + NCW, ... that consumer warp `sw` stages into its slots 2 sw, 2 sw + 1
+  for (int jj = 0;; ++jj) {
+    const int p = sw + NCW * (jj >> 1), h = jj & 1, j = 2 * p + h;
+    if (p >= un.P) break;
+    if (j >= un.rows) continue;
+    const int slot = 2 * sw + h;
+    mbar_wait(&full_d[slot], (p / NCW) & 1);
+    const float4* S = sS + (size_t)slot * SROW;
     const int y = un.y0 + j;
 #pragma unroll 2
     for (int it = 0; it < TW / 4; ++it) {
@@ -490,7 +500,7 @@ __device__ __forceinline__ void scatter_rows(const Args& a, const Unit& un, cons
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_d[sw]);
+    if (lane == 0) mbar_arrive(&empty_d[slot]);
   }
 }
 
@@ -503,8 +513,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_fused_kernel(const Args a) {
   float4* sZ = reinterpret_cast<float4*>(smem + OFF_Z);
   float4* sS = reinterpret_cast<float4*>(smem + OFF_S);
   uint64_t* full_w = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* full_a = full_w + NW;
-  uint64_t* done = full_a + NG;
+  uint64_t* full_a = full_w + 2 * NW;
+  uint64_t* done = full_a + 2 * NG;
   uint64_t* full_d = done + NT;
   uint64_t* empty_d = full_d + NDS;
 
@@ -523,8 +533,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_fused_kernel(const Args a) {
     un.U = 2 * un.P + 2 * R;
   }
   if (tid == 0) {
-    for (int i = 0; i < NW; ++i) mbar_init(&full_w[i], 32);
-    for (int i = 0; i < NG; ++i) mbar_init(&full_a[i], 32);
+    for (int i = 0; i < 2 * NW; ++i) mbar_init(&full_w[i], 32);
+    for (int i = 0; i < 2 * NG; ++i) mbar_init(&full_a[i], 32);
     for (int i = 0; i < NT; ++i) mbar_init(&done[i], 1);
     for (int i = 0; i < NDS; ++i) { mbar_init(&full_d[i], 16); mbar_init(&empty_d[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "fwd_generic.cuh"
 #include "fwd_tile.cuh"
+#include "fwd_mma16.cuh"
 #ifdef PWC_HAVE_STREAM_KERNEL
 #include "fwd_stream.cuh"
 #endif
@@ -142,6 +143,14 @@ int fwd_typed(const void* c1, const void* c2, const void* flow, float flow_scale
     return PWC_OK;
   }
   if (impl >= 2 && !tuned_ok) impl = 1;
+  if (impl == 4) {  // 16-bit band GEMM on the tensor cores (fwd_mma16.cuh): r = 4, C in {32, 64}
+    int rc = 1;
+    if constexpr (sizeof(T) == 2)
+      if (r == 4) rc = pwc::mma16::launch<T, TF>((const T*)c1, (const T*)c2, (const TF*)flow, flow_scale, (T*)out, B, H, W, C, ops, st);
+    if (rc == 0) { PWC_LAUNCH_CHECK(); return PWC_OK; }
+    if (rc < 0) return fail(PWC_ERR_CUDA, "mma16 kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    impl = r == 4 && H >= kTallMinH ? 3 : 2;  // shape not covered
+  }
 #ifdef PWC_HAVE_STREAM_KERNEL
   if (impl == 3) {
     int rc = 1;
@@ -459,7 +468,7 @@ uint64_t pwc_launch_count(void) { return g_launches.load(); }
 int pwc_set_option(const char* key, int value) {
   if (!key) return fail(PWC_ERR_BAD_ARG, "null option key");
   if (!strcmp(key, "fwd_impl")) {
-    if (value < 0 || value > 3) return fail(PWC_ERR_BAD_ARG, "fwd_impl must be 0..3");
+    if (value < 0 || value > 4) return fail(PWC_ERR_BAD_ARG, "fwd_impl must be 0..4");
     g_fwd_impl.store(value);
     return PWC_OK;
   }
