@@ -20,7 +20,8 @@ for impl in ((0,) if os.environ.get("PWC_BWD_ONLY_FUSED") else (1, 0)):
     for k, v in opts:
         _ffi.set_option(k, int(v))
     tot[impl] = 0.0
-    for (lvl, h, w, c) in synth.level_shapes(448, 1024):
+    only = [int(x) for x in os.environ.get("PWC_LEVELS", "6,5,4,3,2").split(",")]
+    for (lvl, h, w, c) in synth.level_shapes(448, 1024, tuple(sorted(only, reverse=True))):
         g = torch.Generator(device=dev).manual_seed(lvl)
         c1 = torch.randn((B, h, w, c), device=dev, generator=g).to(dt)
         c2 = torch.randn((B, h, w, c), device=dev, generator=g).to(dt)

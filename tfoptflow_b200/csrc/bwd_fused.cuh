@@ -42,7 +42,7 @@ constexpr int NW = 18;                      // window ring slots: 4 tasks in fli
 constexpr int NG = 10;                      // A ring slots: 4 tasks x 2 rows in flight, + 2 ahead
 constexpr int NT = 16;                      // task-done barriers
 constexpr int NDS = 8;                      // staged dwarp rows: two (one per half) per consumer warp, drained by its own scatter warp
-constexpr int NCW = 4, NAW = 4;             // consumer / A-producer warps
+constexpr int NCW = 4;                      // consumer warps; the other 12 are split per kernel (template NAW_)
 constexpr int NTHREADS = 512;
 constexpr int REGS_CONSUMER = 200, REGS_OTHER = 104;   // 128 * 200 + 384 * 104 = 512 * 128
 
@@ -100,6 +100,18 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ void bulk_commit_wait_read() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// L2 prefetch of a contiguous span / of one 128-byte line per pixel (the producers are latency-bound: one warp per
+// row with a few dozen loads in flight; pulling the rows of two turns ahead into L2 cuts each exposure from DRAM
+// latency to L2 latency)
+__device__ __forceinline__ void prefetch_span(const void* p, int nbytes, int lane) {
+  const char* c = reinterpret_cast<const char*>(p);
+  for (int o = lane * 128; o < nbytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + o));
+}
+__device__ __forceinline__ void prefetch_pixels(const void* p, int npx, size_t pixel_bytes, int lane) {
+  const char* c = reinterpret_cast<const char*>(p);
+  for (int i = lane; i < npx; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + (size_t)i * pixel_bytes));
 }
 
 // scalar x packed pair (ptxas folds the {a, a} pair into FFMA2's scalar-broadcast operand form)
@@ -178,7 +190,18 @@ __device__ __forceinline__ void produce_window(const Args& a, const Unit& un, fl
   constexpr int NIT = WPX / 4;           // 10
   constexpr int GB = WARP ? 2 : 5;       // steps per gather batch (8 / 5 LDG.128 in flight per lane)
   const T* base = feat + (size_t)un.cs * KS + 4 * f4;
+  auto prefetch_row = [&](int u) {
+    const int y = un.y0 - R + u;
+    if (u >= un.U || y < 0 || y >= a.H) return;
+    const int xlo = max(un.x0 - 2 * R, 0), xhi = min(un.x0 + TW + 2 * R, a.W);
+    const size_t rp = ((size_t)un.b * a.H + y) * a.W + xlo;
+    prefetch_pixels(feat + rp * a.C + (size_t)un.cs * KS, xhi - xlo, (size_t)a.C * sizeof(T), lane);
+    if (WARP) prefetch_span(flow + rp * 2, (xhi - xlo) * 2 * (int)sizeof(TF), lane);
+  };
+  prefetch_row(pi);
+  prefetch_row(pi + NPROD);
   for (int u = pi; u < un.U; u += NPROD) {
+    prefetch_row(u + 2 * NPROD);
     if (u >= NW) wait_window_free(done, u - NW, un.P);
     float4* Wd = sW + (size_t)(u % NW) * WROW;
     const int y = un.y0 - R + u;
@@ -252,13 +275,24 @@ __device__ __forceinline__ void produce_window(const Args& a, const Unit& un, fl
 
 // ---- A producers -------------------------------------------------------------------------------
 // K1: A[d][px] = g * mask / C for strip row j, then the 9 target-row slices go to the workspace by TMA
-template <typename T>
+template <int NAW, typename T>
 __device__ __forceinline__ void produce_a_k1(const Args& a, const Unit& un, float* sA, uint64_t* full_a, uint64_t* done,
                                              int ai, int lane) {
   const T* __restrict__ g = reinterpret_cast<const T*>(a.g);
   const T* __restrict__ out = reinterpret_cast<const T*>(a.out);
   const int psub = lane >> 3, dq = lane & 7;
+  const int npx = min(TW, a.W - un.x0);
+  auto prefetch_row = [&](int j) {
+    if (j >= un.rows) return;
+    const size_t rp = (((size_t)un.b * a.H + un.y0 + j) * a.W + un.x0) * D;
+    prefetch_span(g + rp, npx * D * (int)sizeof(T), lane);
+    prefetch_span(out + rp, npx * D * (int)sizeof(T), lane);
+  };
+  prefetch_row(ai);
+  prefetch_row(ai + NAW);
+  bool pending = false;  // bulk stores of my previous row not yet known to have read their shared-memory source
   for (int j = ai; j < 2 * un.P; j += NAW) {
+    prefetch_row(j + 2 * NAW);
     if (j >= NG) {
       const int p = (j - NG) >> 1;
       mbar_wait(&done[p % NT], (p / NT) & 1);
@@ -301,23 +335,35 @@ __device__ __forceinline__ void produce_a_k1(const Args& a, const Unit& un, floa
     __syncwarp();
     if (j < un.rows) {
       if (lane < ND) {
+        // the previous row's copies have had a whole row's time to read their source; its slot is not rewritten before
+        // the task that uses it has finished (done barrier), which is later still
+        if (pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         const int yq = y + lane - R;  // plane block dyi = lane lands in target row y + dyi - 4
         if (yq >= 0 && yq < a.H)
           bulk_s2g(a.ws + ((((size_t)un.b * a.H + yq) * a.nsx + un.sx) * D + lane * ND) * TW, A + lane * ND * TW,
                    ND * TW * 4);
-        bulk_commit_wait_read();
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
-      __syncwarp();
+      pending = true;
     }
     mbar_arrive(&full_a[j % (2 * NG)]);
   }
+  if (pending && lane < ND) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // before the CTA's memory goes away
 }
 
 // K2: A[ey][ex][px] = g' of the source pixel (row + ey - 4, x + ex - 4) for displacement (8 - ey, 8 - ex),
 // read from the workspace rows of target row y (written by K1 of whichever CTA owned the source rows)
+template <int NAW>
 __device__ __forceinline__ void produce_a_k2(const Args& a, const Unit& un, float* sA, uint64_t* full_a, uint64_t* done,
                                              int ai, int lane) {
+  auto prefetch_row = [&](int j) {  // this strip's tile of target row y0 + j (the neighbour tiles' 4 columns are left to their owners)
+    if (j >= un.rows) return;
+    prefetch_span(a.ws + (((size_t)un.b * a.H + un.y0 + j) * a.nsx + un.sx) * (D * TW), D * TW * 4, lane);
+  };
+  prefetch_row(ai);
+  prefetch_row(ai + NAW);
   for (int j = ai; j < 2 * un.P; j += NAW) {
+    prefetch_row(j + 2 * NAW);
     if (j >= NG) {
       const int p = (j - NG) >> 1;
       mbar_wait(&done[p % NT], (p / NT) & 1);
@@ -449,6 +495,14 @@ __device__ __forceinline__ void scatter_rows(const Args& a, const Unit& un, cons
     if (p >= un.P) break;
     if (j >= un.rows) continue;
     const int slot = 2 * sw + h;
+    {  // corners of the rows this warp scatters next (two tasks ahead), assuming moderate flows
+      const int yn = un.y0 + j + 2 * NCW;
+      if (yn < a.H) {
+        const int xlo = max(un.x0 - 2 * R, 0), xhi = min(un.x0 + TW + 2 * R, a.W);
+        prefetch_pixels(c2 + (((size_t)un.b * a.H + yn) * a.W + xlo) * a.C + (size_t)un.cs * KS, xhi - xlo,
+                        (size_t)a.C * sizeof(T), lane);
+      }
+    }
     mbar_wait(&full_d[slot], (p / NCW) & 1);
     const float4* S = sS + (size_t)slot * SROW;
     const int y = un.y0 + j;
@@ -505,7 +559,9 @@ __device__ __forceinline__ void scatter_rows(const Args& a, const Unit& un, cons
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
-template <int MODE, bool HAS_FLOW, typename T, typename TF>
+// NAW_ = A-producer warps; K1: the other 12 - NAW_ warps gather the warped rows; K2: 4 scatter warps (with a flow) and
+// the rest copy c1 rows
+template <int MODE, bool HAS_FLOW, int NAW_, typename T, typename TF>
 __global__ void __launch_bounds__(NTHREADS, 1) bwd_fused_kernel(const Args a) {
   extern __shared__ __align__(128) unsigned char smem[];
   float4* sW = reinterpret_cast<float4*>(smem + OFF_W);
@@ -548,17 +604,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_fused_kernel(const Args a) {
     return;
   }
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_OTHER));
-  if (warp < NCW + NAW) {
-    if (MODE == 0) produce_a_k1<T>(a, un, reinterpret_cast<float*>(sA), full_a, done, warp - NCW, lane);
-    else produce_a_k2(a, un, reinterpret_cast<float*>(sA), full_a, done, warp - NCW, lane);
+  constexpr int NOTHER = NTHREADS / 32 - NCW - NAW_;
+  if (warp < NCW + NAW_) {
+    if (MODE == 0) produce_a_k1<NAW_, T>(a, un, reinterpret_cast<float*>(sA), full_a, done, warp - NCW, lane);
+    else produce_a_k2<NAW_>(a, un, reinterpret_cast<float*>(sA), full_a, done, warp - NCW, lane);
     return;
   }
-  if (MODE == 0) {  // 8 window producers: the bilinear gather is the heavy producer of K1
-    produce_window<HAS_FLOW, 8, T, TF>(a, un, sW, full_w, done, warp - NCW - NAW, lane);
-  } else if (warp < NCW + NAW + 4) {
-    produce_window<false, 4, T, TF>(a, un, sW, full_w, done, warp - NCW - NAW, lane);
-  } else if (HAS_FLOW) {
-    scatter_rows<T, TF>(a, un, sS, full_d, empty_d, warp - NCW - NAW - 4, lane);
+  const int oi = warp - NCW - NAW_;
+  if (MODE == 0) {
+    produce_window<HAS_FLOW, NOTHER, T, TF>(a, un, sW, full_w, done, oi, lane);
+  } else if (!HAS_FLOW) {
+    produce_window<false, NOTHER, T, TF>(a, un, sW, full_w, done, oi, lane);
+  } else if (oi < NOTHER - NCW) {
+    produce_window<false, NOTHER - NCW, T, TF>(a, un, sW, full_w, done, oi, lane);
+  } else {
+    scatter_rows<T, TF>(a, un, sS, full_d, empty_d, oi - (NOTHER - NCW), lane);
   }
 }
 

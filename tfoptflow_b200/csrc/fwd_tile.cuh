@@ -46,7 +46,7 @@ template <int R, int TWC, int PXC, typename T, typename TF>
 #ifndef PWC_TILE_MAXNREG
 #define PWC_TILE_MAXNREG 96   /* 2 CTAs/SM (9 warps x 96 regs x 2); measured faster than 112 regs x 1 CTA */
 #endif
-__global__ void __maxnreg__(R == 8 ? 112 : (TWC == 32 ? PWC_TILE_MAXNREG : 72))
+__global__ void __maxnreg__(R == 8 ? 96 : (TWC == 32 ? PWC_TILE_MAXNREG : 72))  // r = 8: 17 warps are accounted as 20 (allocation granularity 4): 20 x 32 x 96 <= 64 K
 fwd_tile_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* __restrict__ flow,
                 float flow_scale, T* __restrict__ out, int B, int H, int W, int C,
                 int64_t out_pixel_stride, int tiles_x, int tiles_y) {

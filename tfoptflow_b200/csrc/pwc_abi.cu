@@ -13,6 +13,18 @@
 
 #include "bwd.cuh"
 #include "bwd_fused.cuh"
+#ifndef PWC_BWD_NA1
+#define PWC_BWD_NA1 6    /* K1 with a flow: 6 A producers + 6 gather warps */
+#endif
+#ifndef PWC_BWD_NA1N
+#define PWC_BWD_NA1N 8   /* K1 without a flow: 8 A producers + 4 copy warps */
+#endif
+#ifndef PWC_BWD_NA2
+#define PWC_BWD_NA2 6    /* K2 with a flow: 6 A producers + 2 copy + 4 scatter warps */
+#endif
+#ifndef PWC_BWD_NA2N
+#define PWC_BWD_NA2N 8   /* K2 without a flow: 8 A producers + 4 copy warps */
+#endif
 #include "common.cuh"
 #include "fwd_generic.cuh"
 #include "fwd_tile.cuh"
@@ -377,8 +389,11 @@ int bwd_fused_launch(const void* g, const void* out, const void* c1, const void*
     PWC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf::SMEM_BYTES));
     return PWC_OK;
   };
-  auto k1 = hf ? bf::bwd_fused_kernel<0, true, T, TF> : bf::bwd_fused_kernel<0, false, T, TF>;
-  auto k2 = hf ? bf::bwd_fused_kernel<1, true, T, TF> : bf::bwd_fused_kernel<1, false, T, TF>;
+  // warp split (A producers of 12 non-consumer warps): K1 with a flow also gathers the warped rows, K2 mostly shifts
+  // the transposed g' rows into place
+  constexpr int NA1 = PWC_BWD_NA1, NA1N = PWC_BWD_NA1N, NA2 = PWC_BWD_NA2, NA2N = PWC_BWD_NA2N;
+  auto k1 = hf ? bf::bwd_fused_kernel<0, true, NA1, T, TF> : bf::bwd_fused_kernel<0, false, NA1N, T, TF>;
+  auto k2 = hf ? bf::bwd_fused_kernel<1, true, NA2, T, TF> : bf::bwd_fused_kernel<1, false, NA2N, T, TF>;
   int rc = prep(k1);
   if (rc) return rc;
   if ((rc = prep(k2))) return rc;
