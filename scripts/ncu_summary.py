@@ -4,6 +4,9 @@ rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, vals = rows[0], rows[1], rows[-1]
+for h, v in zip(hdr, vals):
+    if h in ('Kernel Name', 'Block Size', 'Grid Size'):
+        print(f"{h} = {v}")
 keys = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
         'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum',
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st.sum', 'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',

@@ -117,7 +117,11 @@ def test_golden_backward(path, bwd_impl, dev):
     # the sampling coordinate j - flow * scale to fp32 first (4e-6 px at x = 50), which moves the warped features by
     # that much; against the fp32-faithful oracle the same kernels sit at ~1e-6 x rms (the other backward tests)
     assert_close(c1.grad.cpu().numpy(), z["dc1"], 1e-5, f"{name} dc1 (bwd_impl {bwd_impl})", floor=1.0)
-    assert_close(c2.grad.cpu().numpy(), z["dc2"], 1e-5, f"{name} dc2 (bwd_impl {bwd_impl})", floor=1.0)
+    # dc2 is the bilinear scatter of dwarp: its weights are alpha = frac(j - flow * scale), which fp32 (ours and
+    # TensorFlow's) rounds at ulp(j) = 4e-6 .. 8e-6 px in the 64-128 px wide fixtures while the float64 fixture does not.
+    # Measured: 1.7e-5 x rms (2 of 49920 elements beyond 1 rms-tolerance) on the tall case with either implementation,
+    # 1.6e-6 x rms against the fp32-faithful oracle (the other backward tests) - hence a floor of 2 rms-tolerances here.
+    assert_close(c2.grad.cpu().numpy(), z["dc2"], 1e-5, f"{name} dc2 (bwd_impl {bwd_impl})", floor=2.0)
     if flow is not None:
         assert_close(flow.grad.cpu().numpy(), z["dflow"], 1e-5, f"{name} dflow (bwd_impl {bwd_impl})", floor=1.0)
 
@@ -403,7 +407,7 @@ def test_options_round_trip_and_host_path_validation(dev):
     hp = pyramid.HostPyramid()
     hp.run(lv, outs, 4)
     for L, o in zip(lv, outs):
-        ref = O.cost_volume(L["c1"], O.dense_image_warp(L["c2"], L["flow"] * np.float32(L["scaler"])), 4)
+        ref = O.warp_cost_volume(L["c1"], L["c2"], L["flow"], 4, L["scaler"])  # the top level has no flow
         assert_close(o, ref, 1e-2, f"host path fp16 features / fp32 flow level {L['lvl']}")
     bad = [dict(L) for L in lv]
     bad[1]["c2"] = bad[1]["c2"].astype(np.float32)

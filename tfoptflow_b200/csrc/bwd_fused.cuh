@@ -25,6 +25,10 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef PWC_BWD_LANEMAP
+#define PWC_BWD_LANEMAP 1   /* 0: (cg, pg, h) lane order of the first version */
+#endif
+
 namespace pwc {
 namespace bwdf {
 
@@ -408,7 +412,14 @@ template <int MODE, bool HAS_FLOW, typename T>
 __device__ __forceinline__ void consume(const Args& a, const Unit& un, const float4* sW, const float4* sA,
                                         const float4* sZ, float4* sS, uint64_t* full_w, uint64_t* full_a,
                                         uint64_t* done, uint64_t* full_d, uint64_t* empty_d, int warp, int lane) {
+  // Lane order (h, cg, pg) from the lowest bit: every aligned group of 4 lanes reads 2 distinct B words (cg) and 2
+  // distinct A words (h), the pattern the crossbar serves in 2 cycles per LDS.128 (scripts/ubench/lds_pattern.cu);
+  // with (cg, pg, h) the four channel groups of a lane quad made every B load a 4-cycle one.
+#if PWC_BWD_LANEMAP == 0
   const int h = lane >> 4, s = lane & 15, pg = s >> 2, cg = s & 3;
+#else
+  const int h = lane & 1, cg = (lane >> 1) & 3, pg = lane >> 3;
+#endif
   const int g0 = 2 * pg, g1 = 2 * pg + 1;
   for (int p = warp; p < un.P; p += NCW) {
     mbar_wait(&full_a[(2 * p) % (2 * NG)], ((2 * p) / (2 * NG)) & 1);
