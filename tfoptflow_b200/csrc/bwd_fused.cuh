@@ -71,7 +71,8 @@ struct Args {
   float* dflow_acc;     // K2 with flow, several slices: fp32 accumulator (zeroed)
   float* ws;            // transposed g' workspace [B][H][nsx][81][32]
   int B, H, W, C;
-  int nsx, nbands, RB, nslices;
+  int nsx, nslices, NPAIR;   // strips per row, 32-channel slices, row pairs per image
+  long long Q;               // B * nsx * nslices * NPAIR (strip, row pair) units, split evenly over the CTAs
   float flow_scale, inv_c;
 };
 
@@ -168,25 +169,66 @@ struct Unit {
   int b, x0, y0, rows, P, U, cs, sx;   // rows = valid rows of the band, P = row pairs, U = window rows
 };
 
-// wait until every task that reads window row `uold` has finished (tasks are spread round-robin over the NCW consumer
-// warps and complete in order per warp, so the last NCW task indices cover "all tasks <= plast")
-__device__ __forceinline__ void wait_window_free(uint64_t* done, int uold, int P) {
-  int plast = uold >> 1;
-  if (plast > P - 1) plast = P - 1;
+// The kernel is persistent: CTA i owns the units [Q i / G, Q (i + 1) / G) of the linearised (image, strip, slice, row pair)
+// space, cut into per-strip bands, and every warp role walks the same list of bands.  Ring positions and barrier
+// phases are counted GLOBALLY over the CTA's life (tasks: Pb + p, window rows: Ub + u, A rows: 2 (Pb + p) + h), so the
+// producers run ahead into the next band while the consumers finish the current one - no drain / refill between bands.
+struct Walk {
+  long long q, q1;
+  int Pb, Ub;          // tasks / window rows of the bands before the current one
+  int pP, pPb, pUb;    // the previous band: its P and bases (pP == 0: none)
+  __device__ __forceinline__ void init(const Args& a) {
+    q = a.Q * blockIdx.x / gridDim.x;
+    q1 = a.Q * (blockIdx.x + 1) / gridDim.x;
+    Pb = Ub = pP = pPb = pUb = 0;
+  }
+  __device__ __forceinline__ bool next(const Args& a, Unit& un) const {
+    if (q >= q1) return false;
+    const long long strip = q / a.NPAIR;
+    const int p0 = (int)(q - strip * a.NPAIR);
+    const long long rem = q1 - q;
+    const int n = (long long)(a.NPAIR - p0) < rem ? a.NPAIR - p0 : (int)rem;
+    int id = (int)strip;
+    un.cs = id % a.nslices; id /= a.nslices;
+    un.sx = id % a.nsx;
+    un.b = id / a.nsx;
+    un.x0 = un.sx * TW;
+    un.y0 = 2 * p0;
+    un.rows = min(2 * n, a.H - un.y0);
+    un.P = n;
+    un.U = 2 * n + 2 * R;
+    return true;
+  }
+  __device__ __forceinline__ void advance(const Unit& un) {
+    pP = un.P; pPb = Pb; pUb = Ub;
+    Pb += un.P; Ub += un.U; q += un.P;
+  }
+};
+
+// wait until every task that reads the window row with GLOBAL index `ug` has finished.  Row u of a band is read by its
+// tasks p with 2p <= u <= 2p + 9, the last one being min(u / 2, P - 1); tasks are spread round-robin (global index) over
+// the NCW consumer warps and complete in order per warp, so the last NCW task indices cover "all tasks <= plast".
+__device__ __forceinline__ void wait_window_free(uint64_t* done, int ug, const Walk& w, int P) {
+  int plast;
+  if (ug >= w.Ub) plast = w.Pb + min((ug - w.Ub) >> 1, P - 1);
+  else if (w.pP > 0 && ug >= w.pUb) plast = w.pPb + min((ug - w.pUb) >> 1, w.pP - 1);
+  else plast = w.pPb - 1;  // two or more bands back: everything before the previous band
 #pragma unroll
   for (int k = 0; k < NCW; ++k) {
     const int p = plast - k;
     if (p >= 0) mbar_wait(&done[p % NT], (p / NT) & 1);
   }
 }
+// first local index >= 0 whose global index (base + i) is congruent to `me` modulo `n`
+__device__ __forceinline__ int first_mine(int base, int me, int n) { return ((me - base) % n + n) % n; }
 
 // ---- B producers -------------------------------------------------------------------------------
 // window row u <-> image row y0 - 4 + u, pixels x0 - 4 .. x0 + 35, channels [32 cs, 32 cs + 32); zero outside the image.
 // 8 lanes per pixel (one float4 each), 4 pixels per step, 10 steps per row.  The flow of all 10 steps is loaded and
 // turned into corner indices / weights first (one latency exposure), then the corners are gathered GB steps at a time.
 template <bool WARP, int NPROD, typename T, typename TF>
-__device__ __forceinline__ void produce_window(const Args& a, const Unit& un, float4* sW, uint64_t* full_w,
-                                               uint64_t* done, int pi, int lane) {
+__device__ __forceinline__ void produce_window(const Args& a, const Unit& un, const Walk& w, float4* sW,
+                                               uint64_t* full_w, uint64_t* done, int pi, int lane) {
   const T* __restrict__ feat = reinterpret_cast<const T*>(a.feat);
   const TF* __restrict__ flow = reinterpret_cast<const TF*>(a.flow);
   const int psub = lane >> 3, f4 = lane & 7;
@@ -202,12 +244,14 @@ __device__ __forceinline__ void produce_window(const Args& a, const Unit& un, fl
     prefetch_pixels(feat + rp * a.C + (size_t)un.cs * KS, xhi - xlo, (size_t)a.C * sizeof(T), lane);
     if (WARP) prefetch_span(flow + rp * 2, (xhi - xlo) * 2 * (int)sizeof(TF), lane);
   };
-  prefetch_row(pi);
-  prefetch_row(pi + NPROD);
-  for (int u = pi; u < un.U; u += NPROD) {
+  const int u0 = first_mine(w.Ub, pi, NPROD);  // rows are dealt round-robin by GLOBAL index
+  prefetch_row(u0);
+  prefetch_row(u0 + NPROD);
+  for (int u = u0; u < un.U; u += NPROD) {
+    const int ug = w.Ub + u;
     prefetch_row(u + 2 * NPROD);
-    if (u >= NW) wait_window_free(done, u - NW, un.P);
-    float4* Wd = sW + (size_t)(u % NW) * WROW;
+    if (ug >= NW) wait_window_free(done, ug - NW, w, un.P);
+    float4* Wd = sW + (size_t)(ug % NW) * WROW;
     const int y = un.y0 - R + u;
     if (y < 0 || y >= a.H) {
       for (int i = lane; i < WROW; i += 32) Wd[i] = zero;
@@ -273,15 +317,15 @@ __device__ __forceinline__ void produce_window(const Args& a, const Unit& un, fl
         }
       }
     }
-    mbar_arrive(&full_w[u % (2 * NW)]);
+    mbar_arrive(&full_w[ug % (2 * NW)]);
   }
 }
 
 // ---- A producers -------------------------------------------------------------------------------
 // K1: A[d][px] = g * mask / C for strip row j, then the 9 target-row slices go to the workspace by TMA
 template <int NAW, typename T>
-__device__ __forceinline__ void produce_a_k1(const Args& a, const Unit& un, float* sA, uint64_t* full_a, uint64_t* done,
-                                             int ai, int lane) {
+__device__ __forceinline__ void produce_a_k1(const Args& a, const Unit& un, const Walk& w, float* sA, uint64_t* full_a,
+                                             uint64_t* done, int ai, int lane, bool& pending) {
   const T* __restrict__ g = reinterpret_cast<const T*>(a.g);
   const T* __restrict__ out = reinterpret_cast<const T*>(a.out);
   const int psub = lane >> 3, dq = lane & 7;
@@ -292,16 +336,18 @@ __device__ __forceinline__ void produce_a_k1(const Args& a, const Unit& un, floa
     prefetch_span(g + rp, npx * D * (int)sizeof(T), lane);
     prefetch_span(out + rp, npx * D * (int)sizeof(T), lane);
   };
-  prefetch_row(ai);
-  prefetch_row(ai + NAW);
-  bool pending = false;  // bulk stores of my previous row not yet known to have read their shared-memory source
-  for (int j = ai; j < 2 * un.P; j += NAW) {
+  // `pending` (caller's, lives across bands): bulk stores of my previous row not yet known to have read their source
+  const int j0 = first_mine(2 * w.Pb, ai, NAW);
+  prefetch_row(j0);
+  prefetch_row(j0 + NAW);
+  for (int j = j0; j < 2 * un.P; j += NAW) {
+    const int jg = 2 * w.Pb + j;
     prefetch_row(j + 2 * NAW);
-    if (j >= NG) {
-      const int p = (j - NG) >> 1;
+    if (jg >= NG) {
+      const int p = (jg - NG) >> 1;
       mbar_wait(&done[p % NT], (p / NT) & 1);
     }
-    float* A = sA + (size_t)(j % NG) * (AROW * 4);
+    float* A = sA + (size_t)(jg % NG) * (AROW * 4);
     const int y = un.y0 + j;
     if (j >= un.rows) {
       for (int i = lane; i < AROW; i += 32) reinterpret_cast<float4*>(A)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -350,29 +396,30 @@ __device__ __forceinline__ void produce_a_k1(const Args& a, const Unit& un, floa
       }
       pending = true;
     }
-    mbar_arrive(&full_a[j % (2 * NG)]);
+    mbar_arrive(&full_a[jg % (2 * NG)]);
   }
-  if (pending && lane < ND) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // before the CTA's memory goes away
 }
 
 // K2: A[ey][ex][px] = g' of the source pixel (row + ey - 4, x + ex - 4) for displacement (8 - ey, 8 - ex),
 // read from the workspace rows of target row y (written by K1 of whichever CTA owned the source rows)
 template <int NAW>
-__device__ __forceinline__ void produce_a_k2(const Args& a, const Unit& un, float* sA, uint64_t* full_a, uint64_t* done,
-                                             int ai, int lane) {
+__device__ __forceinline__ void produce_a_k2(const Args& a, const Unit& un, const Walk& w, float* sA, uint64_t* full_a,
+                                             uint64_t* done, int ai, int lane) {
   auto prefetch_row = [&](int j) {  // this strip's tile of target row y0 + j (the neighbour tiles' 4 columns are left to their owners)
     if (j >= un.rows) return;
     prefetch_span(a.ws + (((size_t)un.b * a.H + un.y0 + j) * a.nsx + un.sx) * (D * TW), D * TW * 4, lane);
   };
-  prefetch_row(ai);
-  prefetch_row(ai + NAW);
-  for (int j = ai; j < 2 * un.P; j += NAW) {
+  const int j0 = first_mine(2 * w.Pb, ai, NAW);
+  prefetch_row(j0);
+  prefetch_row(j0 + NAW);
+  for (int j = j0; j < 2 * un.P; j += NAW) {
+    const int jg = 2 * w.Pb + j;
     prefetch_row(j + 2 * NAW);
-    if (j >= NG) {
-      const int p = (j - NG) >> 1;
+    if (jg >= NG) {
+      const int p = (jg - NG) >> 1;
       mbar_wait(&done[p % NT], (p / NT) & 1);
     }
-    float* A = sA + (size_t)(j % NG) * (AROW * 4);
+    float* A = sA + (size_t)(jg % NG) * (AROW * 4);
     const int y = un.y0 + j;
     if (j >= un.rows) {
       for (int i = lane; i < AROW; i += 32) reinterpret_cast<float4*>(A)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -401,7 +448,7 @@ __device__ __forceinline__ void produce_a_k2(const Args& a, const Unit& un, floa
           for (int ex = 0; ex < ND; ++ex) A[a_index(lane, (ey0 + q) * ND + ex, ex)] = v[q][ex];
       }
     }
-    mbar_arrive(&full_a[j % (2 * NG)]);
+    mbar_arrive(&full_a[jg % (2 * NG)]);
   }
 }
 
@@ -409,9 +456,10 @@ __device__ __forceinline__ void produce_a_k2(const Args& a, const Unit& un, floa
 // MODE 0: K1, store dc1.  MODE 1: K2; without a flow the rows are dc2 and are stored, with a flow they are staged for
 // the scatter warps.
 template <int MODE, bool HAS_FLOW, typename T>
-__device__ __forceinline__ void consume(const Args& a, const Unit& un, const float4* sW, const float4* sA,
+__device__ __forceinline__ void consume(const Args& a, const Unit& un, const Walk& w, const float4* sW, const float4* sA,
                                         const float4* sZ, float4* sS, uint64_t* full_w, uint64_t* full_a,
-                                        uint64_t* done, uint64_t* full_d, uint64_t* empty_d, int warp, int lane) {
+                                        uint64_t* done, uint64_t* full_d, uint64_t* empty_d, int warp, int lane,
+                                        int& nstaged) {
   // Lane order (h, cg, pg) from the lowest bit: every aligned group of 4 lanes reads 2 distinct B words (cg) and 2
   // distinct A words (h), the pattern the crossbar serves in 2 cycles per LDS.128 (scripts/ubench/lds_pattern.cu);
   // with (cg, pg, h) the four channel groups of a lane quad made every B load a 4-cycle one.
@@ -421,10 +469,11 @@ __device__ __forceinline__ void consume(const Args& a, const Unit& un, const flo
   const int h = lane & 1, cg = (lane >> 1) & 3, pg = lane >> 3;
 #endif
   const int g0 = 2 * pg, g1 = 2 * pg + 1;
-  for (int p = warp; p < un.P; p += NCW) {
-    mbar_wait(&full_a[(2 * p) % (2 * NG)], ((2 * p) / (2 * NG)) & 1);
-    mbar_wait(&full_a[(2 * p + 1) % (2 * NG)], ((2 * p + 1) / (2 * NG)) & 1);
-    const float4* Abase = sA + (size_t)((2 * p + h) % NG) * AROW;
+  for (int p = first_mine(w.Pb, warp, NCW); p < un.P; p += NCW) {
+    const int pg_ = w.Pb + p, jg = 2 * pg_;   // global task / A row index
+    mbar_wait(&full_a[jg % (2 * NG)], (jg / (2 * NG)) & 1);
+    mbar_wait(&full_a[(jg + 1) % (2 * NG)], ((jg + 1) / (2 * NG)) & 1);
+    const float4* Abase = sA + (size_t)((jg + h) % NG) * AROW;
     u64 acc[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -433,7 +482,7 @@ __device__ __forceinline__ void consume(const Args& a, const Unit& un, const flo
 
 #pragma unroll 1
     for (int t = 0; t < ND + 1; ++t) {
-      const int u = 2 * p + t;
+      const int u = w.Ub + 2 * p + t;   // global window row
       mbar_wait(&full_w[u % (2 * NW)], (u / (2 * NW)) & 1);
       const ulonglong2* Wr = reinterpret_cast<const ulonglong2*>(sW + (size_t)(u % NW) * WROW + pg * 65 + 2 * cg);
       const int ey = t - h;  // the two halves use the same window row for different displacements
@@ -463,9 +512,11 @@ __device__ __forceinline__ void consume(const Args& a, const Unit& un, const flo
     const bool rowv = j < un.rows;
     if (MODE == 1 && HAS_FLOW) {
       // this warp's own two staging slots (one per half), drained by scatter warp `warp`: one producer, one consumer
-      const int slot = 2 * warp + h, k = p / NCW;
+      // (`nstaged` = rows this half has staged so far, over all bands: rows past the end of a band are not staged)
+      const int slot = 2 * warp + h;
       if (rowv) {
-        if (k > 0) mbar_wait(&empty_d[slot], (k - 1) & 1);
+        if (nstaged > 0) mbar_wait(&empty_d[slot], (nstaged - 1) & 1);
+        ++nstaged;
         float4* S = sS + (size_t)slot * SROW + pg * 65 + 2 * cg;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -488,24 +539,44 @@ __device__ __forceinline__ void consume(const Args& a, const Unit& un, const flo
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&done[p % NT]);
+    if (lane == 0) mbar_arrive(&done[pg_ % NT]);
   }
 }
 
 // ---- K2 scatter warps ----------------------------------------------------------------------------
 // dense_image_warp backward for one staged dwarp row: 8 lanes per pixel (4 channels each), 4 pixels per step
 template <typename T, typename TF>
-__device__ __forceinline__ void scatter_rows(const Args& a, const Unit& un, const float4* sS, uint64_t* full_d,
-                                             uint64_t* empty_d, int sw, int lane) {
+__device__ __forceinline__ void scatter_rows(const Args& a, const Unit& un, const Walk& w, const float4* sS,
+                                             uint64_t* full_d, uint64_t* empty_d, int sw, int lane, int (&nuse)[2]) {
   const T* __restrict__ c2 = reinterpret_cast<const T*>(a.c2);
   const TF* __restrict__ flow = reinterpret_cast<const TF*>(a.flow);
   const int psub = lane >> 3, f4 = lane & 7;
-  // rows 2p, 2p+1 of the tasks p = sw, sw + NCW, ... that consumer warp `sw` stages into its slots 2 sw, 2 sw + 1
-  for (int jj = 0;; ++jj) {
-    const int p = sw + NCW * (jj >> 1), h = jj & 1, j = 2 * p + h;
-    if (p >= un.P) break;
-    if (j >= un.rows) continue;
+  // rows 2p, 2p+1 of the band's tasks p = pfirst, pfirst + NCW, ... (global index = sw mod NCW) that consumer warp `sw`
+  // stages into its slots 2 sw, 2 sw + 1; nuse[h] = rows taken from slot 2 sw + h so far, over all bands
+  const int pfirst = first_mine(w.Pb, sw, NCW);
+  auto find_row = [&](int& jj) -> bool {  // first jj' >= jj that names a row of the band
+    for (;; ++jj) {
+      const int p = pfirst + NCW * (jj >> 1);
+      if (p >= un.P) return false;
+      if (2 * p + (jj & 1) < un.rows) return true;
+    }
+  };
+  auto load_flow = [&](int jj, TF& f0, TF& f1) {  // flow of this lane's pixel of row jj
+    const int y = un.y0 + 2 * (pfirst + NCW * (jj >> 1)) + (jj & 1);
+    const int x = min(un.x0 + lane, a.W - 1);
+    const size_t pp = ((size_t)un.b * a.H + y) * a.W + x;
+    f0 = flow[2 * pp];
+    f1 = flow[2 * pp + 1];
+  };
+  int jj = 0;
+  bool have = find_row(jj);
+  TF nf0 = TF(0.f), nf1 = TF(0.f);
+  if (have) load_flow(jj, nf0, nf1);
+  while (have) {
+    const int p = pfirst + NCW * (jj >> 1), h = jj & 1, j = 2 * p + h;
     const int slot = 2 * sw + h;
+    int jn = jj + 1;
+    const bool have_next = find_row(jn);
     {  // corners of the rows this warp scatters next (two tasks ahead), assuming moderate flows
       const int yn = un.y0 + j + 2 * NCW;
       if (yn < a.H) {
@@ -514,58 +585,83 @@ __device__ __forceinline__ void scatter_rows(const Args& a, const Unit& un, cons
                         (size_t)a.C * sizeof(T), lane);
       }
     }
-    mbar_wait(&full_d[slot], (p / NCW) & 1);
-    const float4* S = sS + (size_t)slot * SROW;
+    // Latency plan: the flow of the whole row is read once (lane = pixel) and turned into coordinates, then the c2
+    // corners are loaded a quarter row at a time (8 LDG.128 in flight per lane; more does not fit the 104 registers of
+    // this role) - the first quarter BEFORE waiting for the staged dwarp row, so that it overlaps the consumer's work.
     const int y = un.y0 + j;
-#pragma unroll 2
-    for (int it = 0; it < TW / 4; ++it) {
-      const int px = it * 4 + psub, x = un.x0 + px;
-      const bool valid = x < a.W;
-      const int xc = valid ? x : a.W - 1;
-      const SampleCoord sc = sample_coord<T, TF>(flow, a.flow_scale, un.b, y, xc, a.H, a.W);
-      const float ax = sc.ax, ay = sc.ay;
-      const size_t i_tl = (size_t)sc.pix * a.C + un.cs * KS + 4 * f4, i_tr = i_tl + a.C;
-      const size_t i_bl = i_tl + (size_t)a.W * a.C, i_br = i_bl + a.C;
-      float dax = 0.f, day = 0.f;
-      if (valid) {
-        const float4 tl = ld4(c2 + i_tl), tr = ld4(c2 + i_tr), bl = ld4(c2 + i_bl), br = ld4(c2 + i_br);
-        const float4 gw = S[px * 8 + (px >> 3) + f4];
-        const float w_tl = (1.f - ay) * (1.f - ax), w_tr = (1.f - ay) * ax, w_bl = ay * (1.f - ax), w_br = ay * ax;
-        atomicAdd(reinterpret_cast<float4*>(a.acc + i_tl), make_float4(gw.x * w_tl, gw.y * w_tl, gw.z * w_tl, gw.w * w_tl));
-        atomicAdd(reinterpret_cast<float4*>(a.acc + i_tr), make_float4(gw.x * w_tr, gw.y * w_tr, gw.z * w_tr, gw.w * w_tr));
-        atomicAdd(reinterpret_cast<float4*>(a.acc + i_bl), make_float4(gw.x * w_bl, gw.y * w_bl, gw.z * w_bl, gw.w * w_bl));
-        atomicAdd(reinterpret_cast<float4*>(a.acc + i_br), make_float4(gw.x * w_br, gw.y * w_br, gw.z * w_br, gw.w * w_br));
-        const float gv[4] = {gw.x, gw.y, gw.z, gw.w};
-        const float vtl[4] = {tl.x, tl.y, tl.z, tl.w}, vtr[4] = {tr.x, tr.y, tr.z, tr.w};
-        const float vbl[4] = {bl.x, bl.y, bl.z, bl.w}, vbr[4] = {br.x, br.y, br.z, br.w};
+    const SampleCoord sc = sample_coord_v<T, TF>(nf0, nf1, a.flow_scale, un.b, y, min(un.x0 + lane, a.W - 1), a.H, a.W);
+    const float4* S = sS + (size_t)slot * SROW;
+#pragma unroll 1
+    for (int half = 0; half < 4; ++half) {
+      constexpr int NB = TW / 16;  // steps per quarter row
+      float4 tl[NB], tr[NB], bl[NB], br[NB];
+      int pixs[NB];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float top = ax * (vtr[i] - vtl[i]) + vtl[i];
-          const float bot = ax * (vbr[i] - vbl[i]) + vbl[i];
-          dax = fmaf(gv[i], (1.f - ay) * (vtr[i] - vtl[i]) + ay * (vbr[i] - vbl[i]), dax);
-          day = fmaf(gv[i], bot - top, day);
+      for (int k = 0; k < NB; ++k) {
+        const int px = (half * NB + k) * 4 + psub;
+        pixs[k] = __shfl_sync(0xffffffffu, sc.pix, px);
+        const size_t i_tl = (size_t)pixs[k] * a.C + un.cs * KS + 4 * f4;
+        // always a valid address: the coordinates of columns past the image edge were taken at the clamped column
+        tl[k] = ld4(c2 + i_tl);
+        tr[k] = ld4(c2 + i_tl + a.C);
+        bl[k] = ld4(c2 + i_tl + (size_t)a.W * a.C);
+        br[k] = ld4(c2 + i_tl + (size_t)a.W * a.C + a.C);
+      }
+      if (half == 0) {
+        if (have_next) load_flow(jn, nf0, nf1);  // consumed at the top of the next row
+        mbar_wait(&full_d[slot], (h ? nuse[1] : nuse[0]) & 1);
+        if (h) ++nuse[1]; else ++nuse[0];
+      }
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+        const int px = (half * NB + k) * 4 + psub, x = un.x0 + px;
+        const bool valid = x < a.W;
+        const float ax = __shfl_sync(0xffffffffu, sc.ax, px), ay = __shfl_sync(0xffffffffu, sc.ay, px);
+        const float mx = __shfl_sync(0xffffffffu, sc.mx, px), my = __shfl_sync(0xffffffffu, sc.my, px);
+        float dax = 0.f, day = 0.f;
+        if (valid) {
+          const size_t i_tl = (size_t)pixs[k] * a.C + un.cs * KS + 4 * f4, i_tr = i_tl + a.C;
+          const size_t i_bl = i_tl + (size_t)a.W * a.C, i_br = i_bl + a.C;
+          const float4 gw = S[px * 8 + (px >> 3) + f4];
+          const float w_tl = (1.f - ay) * (1.f - ax), w_tr = (1.f - ay) * ax, w_bl = ay * (1.f - ax), w_br = ay * ax;
+          atomicAdd(reinterpret_cast<float4*>(a.acc + i_tl), make_float4(gw.x * w_tl, gw.y * w_tl, gw.z * w_tl, gw.w * w_tl));
+          atomicAdd(reinterpret_cast<float4*>(a.acc + i_tr), make_float4(gw.x * w_tr, gw.y * w_tr, gw.z * w_tr, gw.w * w_tr));
+          atomicAdd(reinterpret_cast<float4*>(a.acc + i_bl), make_float4(gw.x * w_bl, gw.y * w_bl, gw.z * w_bl, gw.w * w_bl));
+          atomicAdd(reinterpret_cast<float4*>(a.acc + i_br), make_float4(gw.x * w_br, gw.y * w_br, gw.z * w_br, gw.w * w_br));
+          const float gv[4] = {gw.x, gw.y, gw.z, gw.w};
+          const float vtl[4] = {tl[k].x, tl[k].y, tl[k].z, tl[k].w}, vtr[4] = {tr[k].x, tr[k].y, tr[k].z, tr[k].w};
+          const float vbl[4] = {bl[k].x, bl[k].y, bl[k].z, bl[k].w}, vbr[4] = {br[k].x, br[k].y, br[k].z, br[k].w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float top = ax * (vtr[i] - vtl[i]) + vtl[i];
+            const float bot = ax * (vbr[i] - vbl[i]) + vbl[i];
+            dax = fmaf(gv[i], (1.f - ay) * (vtr[i] - vtl[i]) + ay * (vbr[i] - vbl[i]), dax);
+            day = fmaf(gv[i], bot - top, day);
+          }
         }
-      }
 #pragma unroll
-      for (int o = 4; o > 0; o >>= 1) {
-        dax += __shfl_xor_sync(0xffffffffu, dax, o);
-        day += __shfl_xor_sync(0xffffffffu, day, o);
-      }
-      if (valid && f4 == 0) {
-        const size_t pidx = ((size_t)un.b * a.H + y) * a.W + x;
-        const float d0 = -day * sc.my * a.flow_scale, d1 = -dax * sc.mx * a.flow_scale;
-        if (a.dflow_acc != nullptr) {
-          atomicAdd(a.dflow_acc + 2 * pidx, d0);
-          atomicAdd(a.dflow_acc + 2 * pidx + 1, d1);
-        } else {
-          TF* df = reinterpret_cast<TF*>(a.dflow);
-          df[2 * pidx] = ElemTraits<TF>::from_f(d0);
-          df[2 * pidx + 1] = ElemTraits<TF>::from_f(d1);
+        for (int o = 4; o > 0; o >>= 1) {
+          dax += __shfl_xor_sync(0xffffffffu, dax, o);
+          day += __shfl_xor_sync(0xffffffffu, day, o);
+        }
+        if (valid && f4 == 0) {
+          const size_t pidx = ((size_t)un.b * a.H + y) * a.W + x;
+          const float d0 = -day * my * a.flow_scale, d1 = -dax * mx * a.flow_scale;
+          if (a.dflow_acc != nullptr) {
+            atomicAdd(a.dflow_acc + 2 * pidx, d0);
+            atomicAdd(a.dflow_acc + 2 * pidx + 1, d1);
+          } else {
+            TF* df = reinterpret_cast<TF*>(a.dflow);
+            df[2 * pidx] = ElemTraits<TF>::from_f(d0);
+            df[2 * pidx + 1] = ElemTraits<TF>::from_f(d1);
+          }
         }
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_d[slot]);
+    jj = jn;
+    have = have_next;
   }
 }
 
@@ -586,19 +682,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_fused_kernel(const Args a) {
   uint64_t* empty_d = full_d + NDS;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  Unit un;
-  {
-    int id = blockIdx.x;
-    un.cs = id % a.nslices; id /= a.nslices;
-    un.sx = id % a.nsx; id /= a.nsx;
-    const int band = id % a.nbands;
-    un.b = id / a.nbands;
-    un.x0 = un.sx * TW;
-    un.y0 = band * a.RB;
-    un.rows = min(a.RB, a.H - un.y0);
-    un.P = (un.rows + 1) >> 1;
-    un.U = 2 * un.P + 2 * R;
-  }
   if (tid == 0) {
     for (int i = 0; i < 2 * NW; ++i) mbar_init(&full_w[i], 32);
     for (int i = 0; i < 2 * NG; ++i) mbar_init(&full_a[i], 32);
@@ -609,34 +692,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_fused_kernel(const Args a) {
   for (int i = tid; i < ASLICE; i += NTHREADS) sZ[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
 
+  // every role walks the CTA's bands in the same order with its own copy of the walk state
+  Walk w;
+  w.init(a);
+  Unit un;
   if (warp < NCW) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_CONSUMER));
-    consume<MODE, HAS_FLOW, T>(a, un, sW, sA, sZ, sS, full_w, full_a, done, full_d, empty_d, warp, lane);
+    int nstaged = 0;
+    while (w.next(a, un)) {
+      consume<MODE, HAS_FLOW, T>(a, un, w, sW, sA, sZ, sS, full_w, full_a, done, full_d, empty_d, warp, lane, nstaged);
+      w.advance(un);
+    }
     return;
   }
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_OTHER));
   constexpr int NOTHER = NTHREADS / 32 - NCW - NAW_;
   if (warp < NCW + NAW_) {
-    if (MODE == 0) produce_a_k1<NAW_, T>(a, un, reinterpret_cast<float*>(sA), full_a, done, warp - NCW, lane);
-    else produce_a_k2<NAW_>(a, un, reinterpret_cast<float*>(sA), full_a, done, warp - NCW, lane);
+    bool pending = false;
+    while (w.next(a, un)) {
+      if (MODE == 0) produce_a_k1<NAW_, T>(a, un, w, reinterpret_cast<float*>(sA), full_a, done, warp - NCW, lane, pending);
+      else produce_a_k2<NAW_>(a, un, w, reinterpret_cast<float*>(sA), full_a, done, warp - NCW, lane);
+      w.advance(un);
+    }
+    // K1: my last bulk stores must have read their shared-memory source before the CTA's memory goes away
+    if (MODE == 0 && pending && lane < ND) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     return;
   }
   const int oi = warp - NCW - NAW_;
-  if (MODE == 0) {
-    produce_window<HAS_FLOW, NOTHER, T, TF>(a, un, sW, full_w, done, oi, lane);
-  } else if (!HAS_FLOW) {
-    produce_window<false, NOTHER, T, TF>(a, un, sW, full_w, done, oi, lane);
-  } else if (oi < NOTHER - NCW) {
-    produce_window<false, NOTHER - NCW, T, TF>(a, un, sW, full_w, done, oi, lane);
-  } else {
-    scatter_rows<T, TF>(a, un, sS, full_d, empty_d, oi - (NOTHER - NCW), lane);
+  int nuse[2] = {0, 0};
+  while (w.next(a, un)) {
+    if (MODE == 0) {
+      produce_window<HAS_FLOW, NOTHER, T, TF>(a, un, w, sW, full_w, done, oi, lane);
+    } else if (!HAS_FLOW) {
+      produce_window<false, NOTHER, T, TF>(a, un, w, sW, full_w, done, oi, lane);
+    } else if (oi < NOTHER - NCW) {
+      produce_window<false, NOTHER - NCW, T, TF>(a, un, w, sW, full_w, done, oi, lane);
+    } else {
+      scatter_rows<T, TF>(a, un, w, sS, full_d, empty_d, oi - (NOTHER - NCW), lane, nuse);
+    }
+    w.advance(un);
   }
 }
 
 // Workspace: transposed g' (fp32), then - with a flow - an fp32 dc2 accumulator for 16-bit tensors and an fp32 dflow
 // accumulator when the channels are processed in several slices.
 struct Plan {
-  int nsx, nbands, RB, nslices;
+  int nsx, nslices, npair;
+  long long Q;   // (image, strip, slice, row pair) units
+  int grid;      // persistent CTAs (one per SM: the kernel uses all of an SM's shared memory)
   size_t ws_off, acc_off, dflow_off, total;
   bool acc_in_ws, dflow_in_ws;
 };
@@ -646,15 +749,12 @@ inline Plan make_plan(int B, int H, int W, int C, size_t elt, size_t flow_elt, b
   Plan p{};
   p.nsx = (W + TW - 1) / TW;
   p.nslices = C / KS;
-  const long long base = (long long)B * p.nsx * p.nslices;
-  long long nb = base > 0 ? (6LL * sms + base - 1) / base : 1;
-  const long long nbmax = H / 14 > 1 ? H / 14 : 1;  // bands shorter than 14 rows pay > 1.5x on the window rows
-  if (nb > nbmax) nb = nbmax;
-  if (nb < 1) nb = 1;
-  int rb = (int)((H + nb - 1) / nb);
-  rb += rb & 1;
-  p.RB = rb;
-  p.nbands = (H + rb - 1) / rb;
+  p.npair = (H + 1) / 2;
+  p.Q = (long long)B * p.nsx * p.nslices * p.npair;
+  // a band shorter than ~4 row pairs pays more for its 8 halo rows than for its own: no more CTAs than that allows
+  long long g = p.Q / 4 > 0 ? p.Q / 4 : 1;
+  if (g > sms) g = sms;
+  p.grid = (int)g;
   size_t off = 0;
   p.ws_off = off;
   off += up256((size_t)B * H * p.nsx * D * TW * 4);

@@ -381,10 +381,10 @@ int bwd_fused_launch(const void* g, const void* out, const void* c1, const void*
   a.g = g; a.out = out; a.flow = flow; a.c2 = c2;
   a.ws = (float*)(base + pl.ws_off);
   a.B = B; a.H = H; a.W = W; a.C = C;
-  a.nsx = pl.nsx; a.nbands = pl.nbands; a.RB = pl.RB; a.nslices = pl.nslices;
+  a.nsx = pl.nsx; a.nslices = pl.nslices; a.NPAIR = pl.npair; a.Q = pl.Q;
   a.flow_scale = scale; a.inv_c = 1.0f / (float)C;
-  const long long grid = (long long)B * pl.nbands * pl.nsx * pl.nslices;
-  if (grid >= (1LL << 31)) return fail(PWC_ERR_BAD_SHAPE, "too many strips");
+  if ((long long)B * pl.nsx * pl.nslices >= (1LL << 31)) return fail(PWC_ERR_BAD_SHAPE, "too many strips");
+  const int grid = pl.grid;  // persistent: one CTA per SM walks its share of the (strip, row pair) units
   auto prep = [&](auto kern) -> int {
     PWC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf::SMEM_BYTES));
     return PWC_OK;
