@@ -71,7 +71,10 @@ uint64_t pwc_launch_count(void);
  *   "stream_prefetch" L2 prefetch distance of the streaming kernel in slabs (default 4, 0 = off)
  *   "stream_debug"    DIAGNOSTICS ONLY, default 0: bits 1 / 2 / 4 skip the correlation / the gathers / the stores
  *                     of the streaming kernel (RESULTS ARE WRONG; bench.py refuses to report with them set), bit 8
- *                     forces the LDG path for c1, bit 16 records the event trace read by pwc_debug_read_trace */
+ *                     forces the LDG path for c1, bit 16 records the event trace read by pwc_debug_read_trace
+ *   "bwd_debug"       DIAGNOSTICS ONLY, default 0: bits 1 / 2 / 4 / 8 / 16 skip the FMA loop / the g, out (K1) or
+ *                     workspace (K2) loads / the window-row loads / the scatter / the workspace stores of the fused
+ *                     backward (RESULTS ARE WRONG; bench.py refuses to report with it set) */
 int pwc_set_option(const char* key, int value);
 int pwc_get_option(const char* key, int* value);
 

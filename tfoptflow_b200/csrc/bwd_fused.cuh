@@ -74,6 +74,8 @@ struct Args {
   int nsx, nslices, NPAIR;   // strips per row, 32-channel slices, row pairs per image
   long long Q;               // B * nsx * nslices * NPAIR (strip, row pair) units, split evenly over the CTAs
   float flow_scale, inv_c;
+  int dbg;   // timing experiments only (option bwd_debug): 1 = no FMA loop, 2 = A rows without loads, 4 = window rows
+             // without loads, 8 = no scatter (K2), 16 = no workspace stores (K1); results are wrong when non-zero
 };
 
 // ---- mbarrier / bulk-copy helpers ------------------------------------------------------------
@@ -253,7 +255,7 @@ __device__ __forceinline__ void produce_window(const Args& a, const Unit& un, co
     if (ug >= NW) wait_window_free(done, ug - NW, w, un.P);
     float4* Wd = sW + (size_t)(ug % NW) * WROW;
     const int y = un.y0 - R + u;
-    if (y < 0 || y >= a.H) {
+    if (y < 0 || y >= a.H || (a.dbg & 4)) {
       for (int i = lane; i < WROW; i += 32) Wd[i] = zero;
     } else {
       int pix[NIT];
@@ -349,7 +351,7 @@ __device__ __forceinline__ void produce_a_k1(const Args& a, const Unit& un, cons
     }
     float* A = sA + (size_t)(jg % NG) * (AROW * 4);
     const int y = un.y0 + j;
-    if (j >= un.rows) {
+    if (j >= un.rows || (a.dbg & 2)) {
       for (int i = lane; i < AROW; i += 32) reinterpret_cast<float4*>(A)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
       const size_t rowpix = ((size_t)un.b * a.H + y) * a.W + un.x0;
@@ -389,7 +391,7 @@ __device__ __forceinline__ void produce_a_k1(const Args& a, const Unit& un, cons
         // the task that uses it has finished (done barrier), which is later still
         if (pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         const int yq = y + lane - R;  // plane block dyi = lane lands in target row y + dyi - 4
-        if (yq >= 0 && yq < a.H)
+        if (yq >= 0 && yq < a.H && !(a.dbg & 16))
           bulk_s2g(a.ws + ((((size_t)un.b * a.H + yq) * a.nsx + un.sx) * D + lane * ND) * TW, A + lane * ND * TW,
                    ND * TW * 4);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -421,7 +423,7 @@ __device__ __forceinline__ void produce_a_k2(const Args& a, const Unit& un, cons
     }
     float* A = sA + (size_t)(jg % NG) * (AROW * 4);
     const int y = un.y0 + j;
-    if (j >= un.rows) {
+    if (j >= un.rows || (a.dbg & 2)) {
       for (int i = lane; i < AROW; i += 32) reinterpret_cast<float4*>(A)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
       const float* __restrict__ wrow = a.ws + ((size_t)un.b * a.H + y) * a.nsx * (D * TW);
@@ -484,6 +486,7 @@ __device__ __forceinline__ void consume(const Args& a, const Unit& un, const Wal
     for (int t = 0; t < ND + 1; ++t) {
       const int u = w.Ub + 2 * p + t;   // global window row
       mbar_wait(&full_w[u % (2 * NW)], (u / (2 * NW)) & 1);
+      if (a.dbg & 1) continue;
       const ulonglong2* Wr = reinterpret_cast<const ulonglong2*>(sW + (size_t)(u % NW) * WROW + pg * 65 + 2 * cg);
       const int ey = t - h;  // the two halves use the same window row for different displacements
       const float4* Ar = (ey >= 0 && ey < ND) ? Abase + ey * ASLICE : sZ;
@@ -602,6 +605,7 @@ __device__ __forceinline__ void scatter_rows(const Args& a, const Unit& un, cons
         pixs[k] = __shfl_sync(0xffffffffu, sc.pix, px);
         const size_t i_tl = (size_t)pixs[k] * a.C + un.cs * KS + 4 * f4;
         // always a valid address: the coordinates of columns past the image edge were taken at the clamped column
+        if (a.dbg & 8) { tl[k] = tr[k] = bl[k] = br[k] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
         tl[k] = ld4(c2 + i_tl);
         tr[k] = ld4(c2 + i_tl + a.C);
         bl[k] = ld4(c2 + i_tl + (size_t)a.W * a.C);
@@ -615,7 +619,7 @@ __device__ __forceinline__ void scatter_rows(const Args& a, const Unit& un, cons
 #pragma unroll
       for (int k = 0; k < NB; ++k) {
         const int px = (half * NB + k) * 4 + psub, x = un.x0 + px;
-        const bool valid = x < a.W;
+        const bool valid = x < a.W && !(a.dbg & 8);
         const float ax = __shfl_sync(0xffffffffu, sc.ax, px), ay = __shfl_sync(0xffffffffu, sc.ay, px);
         const float mx = __shfl_sync(0xffffffffu, sc.mx, px), my = __shfl_sync(0xffffffffu, sc.my, px);
         float dax = 0.f, day = 0.f;

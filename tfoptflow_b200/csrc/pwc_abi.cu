@@ -41,6 +41,7 @@ std::atomic<int> g_fwd_impl{0};
 std::atomic<int> g_stream_ctas{0};
 std::atomic<int> g_stream_pf{4};
 std::atomic<int> g_stream_dbg{0};
+std::atomic<int> g_bwd_dbg{0};   // fused backward: timing experiments only (see bwd_fused.cuh Args::dbg)
 // levels at least this tall take the streaming kernel (it pays ~5 warm-up slabs per strip segment): measured
 // 28 rows 84 us streaming vs 91 us tiled, 14 rows 56 vs 46 us
 constexpr int kTallMinH = 28;
@@ -383,6 +384,7 @@ int bwd_fused_launch(const void* g, const void* out, const void* c1, const void*
   a.B = B; a.H = H; a.W = W; a.C = C;
   a.nsx = pl.nsx; a.nslices = pl.nslices; a.NPAIR = pl.npair; a.Q = pl.Q;
   a.flow_scale = scale; a.inv_c = 1.0f / (float)C;
+  a.dbg = g_bwd_dbg.load();
   if ((long long)B * pl.nsx * pl.nslices >= (1LL << 31)) return fail(PWC_ERR_BAD_SHAPE, "too many strips");
   const int grid = pl.grid;  // persistent: one CTA per SM walks its share of the (strip, row pair) units
   auto prep = [&](auto kern) -> int {
@@ -525,6 +527,10 @@ int pwc_set_option(const char* key, int value) {
     g_stream_dbg.store(value);
     return PWC_OK;
   }
+  if (!strcmp(key, "bwd_debug")) {  // timing experiments only; results are wrong when non-zero
+    g_bwd_dbg.store(value);
+    return PWC_OK;
+  }
   return fail(PWC_ERR_BAD_ARG, "unknown option '%s'", key);
 }
 int pwc_debug_read_trace(void* dst_host, int max_bytes) {
@@ -546,6 +552,7 @@ int pwc_get_option(const char* key, int* value) {
   if (!strcmp(key, "stream_ctas")) { *value = g_stream_ctas.load(); return PWC_OK; }
   if (!strcmp(key, "stream_prefetch")) { *value = g_stream_pf.load(); return PWC_OK; }
   if (!strcmp(key, "stream_debug")) { *value = g_stream_dbg.load(); return PWC_OK; }
+  if (!strcmp(key, "bwd_debug")) { *value = g_bwd_dbg.load(); return PWC_OK; }
   if (!strcmp(key, "overlap_levels")) { *value = g_overlap.load(); return PWC_OK; }
   if (!strcmp(key, "bwd_impl")) { *value = g_bwd_impl.load(); return PWC_OK; }
   if (!strcmp(key, "side_sms")) { *value = g_side_sms.load(); return PWC_OK; }
