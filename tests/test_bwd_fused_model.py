@@ -1,5 +1,5 @@
 """CPU model of the fused backward's data flow (tfoptflow_b200/csrc/bwd_fused.cuh): the A-row layout with its bank
-swizzle, the target-row-indexed workspace K1 writes and K2 reads shifted, the 9-row window and the skewed row-pair
+swizzle, the target-row-indexed workspace tensor K1 stores its plane blocks into and K2 loads shifted boxes from, the 9-row window and the skewed row-pair
 walk of the consumer.  It is checked against the oracle, so an indexing mistake in the design shows up here, on the
 CPU, before any GPU time is spent; the CUDA code itself is checked by tests/test_gpu_parity.py."""
 import numpy as np
@@ -25,6 +25,33 @@ def test_a_index_is_a_bijection_and_builder_stores_are_conflict_free():
             assert len(set(banks)) >= 28
 
 
+def store_row_blocks(ws, gp, b, x0, y, H, W):
+    """bwd_fused.cuh produce_a_k1: plane block dyi of SOURCE row y goes, at the source's own x, to TARGET row y + dyi - 4
+    of the workspace tensor [B][H][dyi][dxi][x] (one tensor store per block, clipped at the image edge); the blocks of
+    target row y whose source row y + 4 - dyi is outside the image are written as zeros."""
+    n = min(TW, W - x0)
+    for dyi in range(ND):
+        yq = y + dyi - R
+        if 0 <= yq < H:
+            assert np.isnan(ws[b, yq, dyi, :, x0:x0 + n]).all(), "workspace block written twice"
+            ws[b, yq, dyi, :, x0:x0 + n] = gp[b, y, x0:x0 + n, dyi * ND:(dyi + 1) * ND].T
+        if not 0 <= y + R - dyi < H:
+            assert np.isnan(ws[b, y, dyi, :, x0:x0 + n]).all(), "workspace block written twice"
+            ws[b, y, dyi, :, x0:x0 + n] = 0.0
+
+
+def load_a_row(ws, b, x0, y, W):
+    """produce_a_k2: 9 tensor loads, box (x0 + ex - 4 .. + 31, dxi = 8 - ex, dyi = 0 .. 8, row y), zero outside [0, W)"""
+    A = np.zeros(D * TW)
+    for ex in range(ND):
+        for px in range(TW):
+            xs = x0 + px + ex - R
+            for ey in range(ND):
+                v = ws[b, y, 2 * R - ey, 2 * R - ex, xs] if 0 <= xs < W else 0.0
+                A[a_index(px, ey * ND + ex, ex)] = v
+    return A
+
+
 def consumer(A_rows, win, P):
     """A_rows[j] : [81*32] swizzled planes of band row j; win[u] : [40, C] window rows -> out[j][px][c].
     Row pair p: half h handles row 2p + h with ey = t - h at step t, window row u = 2p + t (same for both halves)."""
@@ -43,7 +70,7 @@ def consumer(A_rows, win, P):
     return out
 
 
-@pytest.mark.parametrize("shape", [(1, 10, 40, 32, 6), (2, 7, 33, 32, 4)])
+@pytest.mark.parametrize("shape", [(1, 10, 40, 32, 6), (2, 7, 33, 32, 4), (1, 6, 64, 32, 4), (1, 9, 20, 32, 6), (1, 3, 35, 32, 2)])
 def test_model_matches_oracle(shape):
     B, H, W, C, RB = shape
     d = synth.make_level(B, H, W, C, 5, np.float32, "smooth", with_grad=True)
@@ -54,7 +81,7 @@ def test_model_matches_oracle(shape):
     gp = (g * np.where(outf > 0, 1.0, 0.1)).astype(np.float64) / C
     nsx = (W + TW - 1) // TW
     nb = (H + RB - 1) // RB
-    ws = np.full((B, H, nsx, D * TW), np.nan)   # never-written entries must not be used
+    ws = np.full((B, H, ND, ND, W), np.nan)   # never-written entries must not be used
     dc1 = np.zeros_like(dc1_ref, dtype=np.float64)
     dwarp = np.zeros_like(dc1)
 
@@ -84,30 +111,17 @@ def test_model_matches_oracle(shape):
                 if x0 + px < W:
                     for dd in range(D):
                         A[j][a_index(px, dd, dd % ND)] = gp[b, y0 + j, x0 + px, dd]
-            for dyi in range(ND):   # bulk copies: plane block dyi -> target row y + dyi - 4
-                yq = y0 + j + dyi - R
-                if 0 <= yq < H:
-                    ws[b, yq, sx, dyi * ND * TW:(dyi + 1) * ND * TW] = A[j][dyi * ND * TW:(dyi + 1) * ND * TW]
+            store_row_blocks(ws, gp, b, x0, y0 + j, H, W)
         o = consumer(A, window(warp, b, x0, y0, P), P)
         for j in range(rows):
             n = min(TW, W - x0)
             dc1[b, y0 + j, x0:x0 + n] = o[j][:n]
-    # ---- K2
+    # ---- K2: the A row of dwarp row y, strip sx is the workspace tile as it is (one bulk copy)
     for b, sx, x0, y0, rows, P in units():
         A = np.zeros((2 * P, D * TW))
         for j in range(rows):
-            y = y0 + j
-            for ey in range(ND):
-                ys = y + ey - R
-                for ex in range(ND):
-                    for px in range(TW):
-                        xs = x0 + px + ex - R
-                        v = 0.0
-                        if 0 <= ys < H and 0 <= xs < W:
-                            dxi = 2 * R - ex
-                            v = ws[b, y, xs >> 5, a_index(xs & 31, (2 * R - ey) * ND + dxi, dxi)]
-                        A[j][a_index(px, ey * ND + ex, ex)] = v
-        assert np.isfinite(A).all(), "K2 read a workspace entry K1 never wrote"
+            A[j] = load_a_row(ws, b, x0, y0 + j, W)
+            assert np.isfinite(A[j]).all(), "K2 read a workspace entry K1 never wrote"
         o = consumer(A, window(c1, b, x0, y0, P), P)
         for j in range(rows):
             n = min(TW, W - x0)

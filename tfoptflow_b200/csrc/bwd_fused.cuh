@@ -9,20 +9,24 @@
 // banded correlation of 81 scalar planes A against a 9-row window of feature rows.  One consumer routine serves both:
 //   * a CTA owns (image, 32-pixel strip, band of rows, 32-channel slice) and marches down the band;
 //   * B rows live in a shared-memory ring (K1: rows of c2 warped on the fly by gather warps, never in HBM; K2: rows of c1);
-//   * A rows (81 x 32 fp32 per strip row, [d][px]) live in a second ring.  K1 builds them from g and out, and also
-//     writes them, as they are, to a workspace indexed by TARGET row (9 bulk shared->global copies per row, TMA
-//     `cp.async.bulk`): that is g' transposed for K2, which only has to shift it by ex - 4 pixels when loading;
+//   * A rows (81 x 32 fp32 per strip row) live in a second ring.  K1 builds them from g and out and also sends them, as
+//     they are, to a workspace tensor [B * H (TARGET row)][dyi][dxi][x]: 9 TMA tensor stores per row (one plane block
+//     per target row, whole 128-byte lines).  K2 fetches the A row of a dwarp row from there with TMA tensor loads that
+//     start ex - 4 pixels to the side, rounded down to a multiple of 4 (tensor copies want 16-byte aligned starts), and
+//     shifts the remaining 0..3 pixels in shared memory;
 //   * 4 consumer warps (one per scheduler) each own a PAIR of output rows: lanes 0-15 row 2p, lanes 16-31 row 2p+1,
 //     8 pixels x 8 channels per lane (32 packed f32x2 accumulators).  The two halves walk the window skewed by one
 //     row, so both read the SAME window row in every step: the B operand (LDS.128, the expensive one) is shared by
 //     the two halves, the A operand is a scalar-broadcast FFMA2 source shared by the 4 channel groups of a pixel group.
-//   * K2 hands finished dwarp rows to 4 scatter warps (red.global.add.v4.f32 into an fp32 dc2, warp-shuffle dflow).
+//   * K2 hands finished dwarp rows to 8 scatter warps, one per staging slot (red.global.add.v4.f32 into an fp32 dc2,
+//     warp-shuffle dflow).
 // Synchronisation: mbarriers only (full per ring slot, done per task); no __syncthreads after the role split.
 // A parity wait also passes when the barrier is one whole phase BEHIND the one waited for (the parity then names the
 // preceding phase), so every barrier here has either a single producer and a single consumer that alternate strictly
 // (staging slots), or two alternating barrier sets per data slot (rings: index i % 2N, parity (i / 2N) & 1), or a
 // dependency chain that keeps waiters less than one lap ahead (task-done barriers, see wait_window_free).
 #pragma once
+#include <cuda.h>   // CUtensorMap (types only: the encode entry point is fetched through the runtime)
 #include "common.cuh"
 
 #ifndef PWC_BWD_LANEMAP
@@ -42,22 +46,32 @@ constexpr int WROW = WPX * 8 + WPX / 8;     // float4 per window row: 8 per pixe
 constexpr int AROW = D * TW / 4;            // float4 per A row
 constexpr int ASLICE = ND * TW / 4;         // float4 per (row, ey) slice
 constexpr int SROW = TW * 8 + TW / 8;       // float4 per staged dwarp row (same padding as the window)
-constexpr int NW = 18;                      // window ring slots: 4 tasks in flight span 16 rows, + 2 ahead
 constexpr int NG = 10;                      // A ring slots: 4 tasks x 2 rows in flight, + 2 ahead
 constexpr int NT = 16;                      // task-done barriers
 constexpr int NDS = 8;                      // staged dwarp rows: two (one per half) per consumer warp, drained by its own scatter warp
 constexpr int NCW = 4;                      // consumer warps; the other 12 are split per kernel (template NAW_)
 constexpr int NTHREADS = 512;
 constexpr int REGS_CONSUMER = 200, REGS_OTHER = 104;   // 128 * 200 + 384 * 104 = 512 * 128
+constexpr int AREM = 2 * 512;               // K2: the two remainder boxes of an A row (2 x 432 bytes, 128-byte aligned)
 
-constexpr size_t OFF_W = 0;
-constexpr size_t OFF_A = OFF_W + (size_t)NW * WROW * 16;
-constexpr size_t OFF_Z = OFF_A + (size_t)NG * AROW * 16;
-constexpr size_t OFF_S = OFF_Z + (size_t)ASLICE * 16;
-constexpr size_t OFF_BAR = OFF_S + (size_t)NDS * SROW * 16;
-constexpr int NBAR = 2 * NW + 2 * NG + NT + 2 * NDS;
-constexpr size_t SMEM_BYTES = OFF_BAR + (size_t)NBAR * 8;
-static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+// Shared-memory layout per kernel.  K1: 18 window rows (4 tasks in flight span 16, + 2 ahead).  K2: its A slots also
+// hold the remainder boxes, paid for with a 16-row window ring (the two rows a task frees are needed by the same warp's
+// next task only in its last two steps)
+template <int MODE>
+struct Lay {
+  static constexpr int NW = MODE == 0 ? 18 : 16;
+  static constexpr size_t ASTRIDE = (size_t)AROW * 16 + (MODE == 0 ? 0 : AREM);   // bytes per A slot
+  static constexpr size_t OFF_A = 0;                 // TMA tensor source / destination: 128-byte aligned slots
+  static constexpr size_t OFF_Z = OFF_A + (size_t)NG * ASTRIDE;
+  static constexpr size_t OFF_W = OFF_Z + (size_t)ASLICE * 16;
+  static constexpr size_t OFF_S = OFF_W + (size_t)NW * WROW * 16;
+  static constexpr size_t OFF_BAR = OFF_S + (size_t)NDS * SROW * 16;
+  static constexpr int NBAR = 2 * NW + 2 * NG + NT + 2 * NDS + (MODE == 0 ? 0 : 2 * NG);
+  static constexpr size_t SMEM_BYTES = OFF_BAR + (size_t)NBAR * 8;
+  static_assert(ASTRIDE % 128 == 0 && OFF_Z % 128 == 0 && (ND * TW * 4) % 128 == 0, "TMA tensor copies want 128-byte aligned shared memory");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+};
+constexpr size_t SMEM_BYTES = Lay<0>::SMEM_BYTES > Lay<1>::SMEM_BYTES ? Lay<0>::SMEM_BYTES : Lay<1>::SMEM_BYTES;
 
 struct Args {
   const void* g;        // K1: upstream gradient [B,H,W,81]
@@ -69,9 +83,10 @@ struct Args {
   float* acc;           // K2 with flow: fp32 dc2 accumulator (zeroed)
   void* dflow;          // K2 with flow, single slice: flow gradient
   float* dflow_acc;     // K2 with flow, several slices: fp32 accumulator (zeroed)
-  float* ws;            // transposed g' workspace [B][H][nsx][81][32]
+  float* ws;            // g' workspace, the tensor [B * H (target row)][dyi][dxi][wpitch] behind the kernels' tensor map
   int B, H, W, C;
   int nsx, nslices, NPAIR;   // strips per row, 32-channel slices, row pairs per image
+  int wpitch;                // row pitch of a workspace plane in floats (W rounded up to 4)
   long long Q;               // B * nsx * nslices * NPAIR (strip, row pair) units, split evenly over the CTAs
   float flow_scale, inv_c;
   int dbg;   // timing experiments only (option bwd_debug): 1 = no FMA loop, 2 = A rows without loads, 4 = window rows
@@ -104,6 +119,33 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t by
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
                : "memory");
 }
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// TMA tensor copies (SASS: UTMALDG / UTMASTG), 4-d, coordinates innermost first
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(tm)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_commit_wait_read() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -134,9 +176,11 @@ __device__ __forceinline__ float2 unpack2(u64 v) {
 }
 __device__ __forceinline__ float comp(const float4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
 
-// float index of (pixel px, plane d) inside an A row: [d][px], the 8 float4 groups of a plane XOR-ed with (d % 9) & 7 so
-// that the builder's stores (lanes = 4 pixels x 8 consecutive planes) hit 32 distinct banks
-__device__ __forceinline__ int a_index(int px, int d, int ex) { return d * TW + ((((px >> 2) ^ (ex & 7)) << 2) | (px & 3)); }
+// float index of (pixel px, plane d) inside a K1 A row: [d][px], the 8 float4 groups of a plane XOR-ed with key & 7, where
+// key = slot + d = bits 7..9 of the element's shared-memory address (the A ring starts at a 1024-byte boundary, a slot
+// is 81 x 128 bytes, a plane 128 bytes): the TMA unit's 128-byte swizzle, which the tensor stores undo on the way out.
+// The builder's stores (lanes = 4 pixels x 8 consecutive planes) hit 32 distinct banks with it.
+__device__ __forceinline__ int a_index(int px, int d, int key) { return d * TW + ((((px >> 2) ^ (key & 7)) << 2) | (px & 3)); }
 
 template <typename T>
 __device__ __forceinline__ float ld1(const T* p) { return ElemTraits<T>::to_f(__ldg(p)); }
@@ -228,7 +272,7 @@ __device__ __forceinline__ int first_mine(int base, int me, int n) { return ((me
 // window row u <-> image row y0 - 4 + u, pixels x0 - 4 .. x0 + 35, channels [32 cs, 32 cs + 32); zero outside the image.
 // 8 lanes per pixel (one float4 each), 4 pixels per step, 10 steps per row.  The flow of all 10 steps is loaded and
 // turned into corner indices / weights first (one latency exposure), then the corners are gathered GB steps at a time.
-template <bool WARP, int NPROD, typename T, typename TF>
+template <bool WARP, int NPROD, int NW, typename T, typename TF>
 __device__ __forceinline__ void produce_window(const Args& a, const Unit& un, const Walk& w, float4* sW,
                                                uint64_t* full_w, uint64_t* done, int pi, int lane) {
   const T* __restrict__ feat = reinterpret_cast<const T*>(a.feat);
@@ -236,7 +280,7 @@ __device__ __forceinline__ void produce_window(const Args& a, const Unit& un, co
   const int psub = lane >> 3, f4 = lane & 7;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
   constexpr int NIT = WPX / 4;           // 10
-  constexpr int GB = WARP ? 2 : 5;       // steps per gather batch (8 / 5 LDG.128 in flight per lane)
+  constexpr int GB = WARP ? 2 : 10;      // steps per gather batch (8 / 10 LDG.128 in flight per lane)
   const T* base = feat + (size_t)un.cs * KS + 4 * f4;
   auto prefetch_row = [&](int u) {
     const int y = un.y0 - R + u;
@@ -324,10 +368,21 @@ __device__ __forceinline__ void produce_window(const Args& a, const Unit& un, co
 }
 
 // ---- A producers -------------------------------------------------------------------------------
-// K1: A[d][px] = g * mask / C for strip row j, then the 9 target-row slices go to the workspace by TMA
+// K1: A[d][px] = g * mask / C for strip row j, then the 9 plane blocks go to the workspace by TMA tensor stores.
+//
+// Workspace: a 4-d fp32 tensor [B * H (TARGET row)][dyi 9][dxi 9][x] over the whole image width (row pitch W rounded up
+// to 4).  Plane block dyi of SOURCE row y lands in target row y + dyi - 4, at the source's own x: one tensor store per
+// block (box 32 x 9 planes, whole aligned 128-byte lines - no partial sectors), clipped at the image edge by the
+// tensor map.  The K2 consumer wants, for dwarp row y and strip x0, A[ey][ex][px] = g' of the source pixel
+// (y + ey - 4, x0 + px + ex - 4) for displacement (8 - ey, 8 - ex): that is the box (x0 + ex - 4, dxi = 8 - ex,
+// dyi = 0 .. 8, row y) of this tensor, so K2 fetches an A row with 9 tensor loads that start at an arbitrary x - the
+// TMA unit does the shift and zero-fills what lies outside the image.  Blocks whose source row is outside the image
+// are written as zeros (from sZ) by the builder of the row that shares their index.
+// The A slot is swizzled the way the tensor map's 128-byte mode expects (16-byte chunk ^= bits 7..9 of the address).
 template <int NAW, typename T>
 __device__ __forceinline__ void produce_a_k1(const Args& a, const Unit& un, const Walk& w, float* sA, uint64_t* full_a,
-                                             uint64_t* done, int ai, int lane, bool& pending) {
+                                             const float4* sZ, uint64_t* done, int ai, int lane, bool& pending,
+                                             const CUtensorMap* tm) {
   const T* __restrict__ g = reinterpret_cast<const T*>(a.g);
   const T* __restrict__ out = reinterpret_cast<const T*>(a.out);
   const int psub = lane >> 3, dq = lane & 7;
@@ -349,7 +404,8 @@ __device__ __forceinline__ void produce_a_k1(const Args& a, const Unit& un, cons
       const int p = (jg - NG) >> 1;
       mbar_wait(&done[p % NT], (p / NT) & 1);
     }
-    float* A = sA + (size_t)(jg % NG) * (AROW * 4);
+    const int slot = jg % NG;
+    float* A = sA + (size_t)slot * (AROW * 4);
     const int y = un.y0 + j;
     if (j >= un.rows || (a.dbg & 2)) {
       for (int i = lane; i < AROW; i += 32) reinterpret_cast<float4*>(A)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -378,7 +434,7 @@ __device__ __forceinline__ void produce_a_k1(const Args& a, const Unit& un, cons
 #pragma unroll
           for (int o = 0; o < 11; ++o) {
             const int d = o * 8 + dq;
-            if (d < D) A[a_index(px, d, d % ND)] = (gv[q][o] * (ov[q][o] > 0.0f ? 1.0f : 0.1f)) * a.inv_c;
+            if (d < D) A[a_index(px, d, slot + d)] = (gv[q][o] * (ov[q][o] > 0.0f ? 1.0f : 0.1f)) * a.inv_c;
           }
         }
       }
@@ -391,9 +447,10 @@ __device__ __forceinline__ void produce_a_k1(const Args& a, const Unit& un, cons
         // the task that uses it has finished (done barrier), which is later still
         if (pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         const int yq = y + lane - R;  // plane block dyi = lane lands in target row y + dyi - 4
-        if (yq >= 0 && yq < a.H && !(a.dbg & 16))
-          bulk_s2g(a.ws + ((((size_t)un.b * a.H + yq) * a.nsx + un.sx) * D + lane * ND) * TW, A + lane * ND * TW,
-                   ND * TW * 4);
+        if (yq >= 0 && yq < a.H && !(a.dbg & 16)) tma_store_4d(tm, A + lane * ND * TW, un.x0, 0, lane, un.b * a.H + yq);
+        // target row y itself: block dyi = lane would come from source row y + 4 - dyi
+        const int ys = y + R - lane;
+        if ((ys < 0 || ys >= a.H) && !(a.dbg & 16)) tma_store_4d(tm, sZ, un.x0, 0, lane, un.b * a.H + y);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
       pending = true;
@@ -402,55 +459,78 @@ __device__ __forceinline__ void produce_a_k1(const Args& a, const Unit& un, cons
   }
 }
 
-// K2: A[ey][ex][px] = g' of the source pixel (row + ey - 4, x + ex - 4) for displacement (8 - ey, 8 - ex),
-// read from the workspace rows of target row y (written by K1 of whichever CTA owned the source rows)
-template <int NAW>
-__device__ __forceinline__ void produce_a_k2(const Args& a, const Unit& un, const Walk& w, float* sA, uint64_t* full_a,
-                                             uint64_t* done, int ai, int lane) {
-  auto prefetch_row = [&](int j) {  // this strip's tile of target row y0 + j (the neighbour tiles' 4 columns are left to their owners)
-    if (j >= un.rows) return;
-    prefetch_span(a.ws + (((size_t)un.b * a.H + un.y0 + j) * a.nsx + un.sx) * (D * TW), D * TW * 4, lane);
-  };
-  const int j0 = first_mine(2 * w.Pb, ai, NAW);
-  prefetch_row(j0);
-  prefetch_row(j0 + NAW);
-  for (int j = j0; j < 2 * un.P; j += NAW) {
-    const int jg = 2 * w.Pb + j;
-    prefetch_row(j + 2 * NAW);
-    if (jg >= NG) {
-      const int p = (jg - NG) >> 1;
-      mbar_wait(&done[p % NT], (p / NT) & 1);
-    }
-    float* A = sA + (size_t)(jg % NG) * (AROW * 4);
-    const int y = un.y0 + j;
-    if (j >= un.rows || (a.dbg & 2)) {
-      for (int i = lane; i < AROW; i += 32) reinterpret_cast<float4*>(A)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    } else {
-      const float* __restrict__ wrow = a.ws + ((size_t)un.b * a.H + y) * a.nsx * (D * TW);
+// K2: A[ex][dyi][px] = g' of the source pixel (y + 4 - dyi, x0 + px + ex - 4) for displacement (dyi, dxi = 8 - ex) = plane
+// (dyi, 8 - ex) of workspace row y at x = x0 + px + s, s = ex - 4.  A tensor load must start at a multiple of 16 bytes
+// (a box at any other x faults: scripts/ubench/tma_tensor_probe.cu), so the TMA unit does the coarse part of the shift,
+// c = 4 floor(s / 4) in {-4, 0, 4}: one box (32 px x 9 dyi) per ex at x0 + c, plus two small boxes (4 px x 3 planes x
+// 9 dyi) with the 4 pixels that follow the main boxes of ex = 1..3 and ex = 5..7.  The remaining r = s - c = ex & 3 pixels
+// are shifted in place, in shared memory, by the warp that issued the copies (54 rows of 32 floats: lane = pixel, all
+// rows read, then all rows written).  No global latency is exposed: the copies of a warp's next row are in flight
+// while it shifts the current one.  landed[] counts the copies' bytes, full_a is the hand-over to the consumers.
+constexpr uint32_t A_TX_BYTES = D * TW * 4 + 2 * (4 * 3 * ND * 4);
+__device__ __forceinline__ void k2_issue_row(const Args& a, const Unit& un, int j, int jg, unsigned char* sA,
+                                             uint64_t* landed, uint64_t* done, int lane, const CUtensorMap* tm_main,
+                                             const CUtensorMap* tm_rem, int pf) {
+  if (jg >= NG) {
+    const int p = (jg - NG) >> 1;
+    mbar_wait(&done[p % NT], (p / NT) & 1);
+  }
+  if (j >= un.rows || (a.dbg & 2)) return;   // a zero row: filled at hand-over time
+  if (lane == 0) {
+    unsigned char* A = sA + (size_t)(jg % NG) * Lay<1>::ASTRIDE;
+    uint64_t* bar = &landed[jg % (2 * NG)];
+    const int row = un.b * a.H + un.y0 + j;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the consumers' reads of the slot come first
+    mbar_arrive_expect_tx(bar, A_TX_BYTES);
 #pragma unroll 1
-      for (int ey0 = 0; ey0 < ND; ey0 += 3) {   // 27 loads in flight per lane
-        float v[3][ND];
+    for (int ex = 0; ex < ND; ++ex)
+      tma_load_4d(A + ex * (ND * TW * 4), tm_main, bar, un.x0 + ((ex - R) & ~3), 2 * R - ex, 0, row);
+    // ex = 1..3 (c = -4): pixels x0 + 28 .. 31 of planes dxi = 7, 6, 5;  ex = 5..7 (c = 0): x0 + 32 .. 35 of dxi = 3, 2, 1
+    tma_load_4d(A + AROW * 16, tm_rem, bar, un.x0 + TW - R, 5, 0, row);
+    tma_load_4d(A + AROW * 16 + AREM / 2, tm_rem, bar, un.x0 + TW, 1, 0, row);
+  } else if (lane <= ND && j + pf < un.rows) {
+    // pull a row further down the band into L2: lanes 1..9 take one main box each (the remainder boxes share its lines)
+    const int ex = lane - 1;
+    tma_prefetch_4d(tm_main, un.x0 + ((ex - R) & ~3), 2 * R - ex, 0, un.b * a.H + un.y0 + j + pf);
+  }
+}
+__device__ __forceinline__ void k2_finish_row(const Args& a, const Unit& un, int j, int jg, unsigned char* sA,
+                                              uint64_t* landed, uint64_t* full_a, int lane) {
+  float* A = reinterpret_cast<float*>(sA + (size_t)(jg % NG) * Lay<1>::ASTRIDE);
+  if (j >= un.rows || (a.dbg & 2)) {
+    for (int i = lane; i < AROW; i += 32) reinterpret_cast<float4*>(A)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    mbar_wait(&landed[jg % (2 * NG)], (jg / (2 * NG)) & 1);
+    const float* rem = A + AROW * 4;
+    float v[6 * ND];
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          const int ey = ey0 + q, ys = y + ey - R;
-          const bool rv = ys >= 0 && ys < a.H;
+    for (int k = 0; k < 6; ++k) {
+      const int ex = k < 3 ? k + 1 : k + 2, r = ex & 3;          // 1, 2, 3, 5, 6, 7
+      const float* rbox = rem + (k < 3 ? 0 : AREM / 8);           // [dyi][3 planes][4 px]; plane dxi = 8 - ex is box plane 3 - r
 #pragma unroll
-          for (int ex = 0; ex < ND; ++ex) {
-            const int xs = un.x0 + lane + ex - R;
-            v[q][ex] = 0.f;
-            if (rv && xs >= 0 && xs < a.W) {
-              const int dxi = 2 * R - ex;
-              v[q][ex] = __ldg(wrow + (size_t)(xs >> 5) * (D * TW) + a_index(xs & 31, (2 * R - ey) * ND + dxi, dxi));
-            }
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < 3; ++q)
-#pragma unroll
-          for (int ex = 0; ex < ND; ++ex) A[a_index(lane, (ey0 + q) * ND + ex, ex)] = v[q][ex];
-      }
+      for (int dyi = 0; dyi < ND; ++dyi)
+        v[k * ND + dyi] = lane + r < TW ? A[(ex * ND + dyi) * TW + lane + r] : rbox[(dyi * 3 + (3 - r)) * 4 + lane + r - TW];
     }
-    mbar_arrive(&full_a[jg % (2 * NG)]);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const int ex = k < 3 ? k + 1 : k + 2;
+#pragma unroll
+      for (int dyi = 0; dyi < ND; ++dyi) A[(ex * ND + dyi) * TW + lane] = v[k * ND + dyi];
+    }
+  }
+  mbar_arrive(&full_a[jg % (2 * NG)]);
+}
+template <int NAW>
+__device__ __forceinline__ void produce_a_k2(const Args& a, const Unit& un, const Walk& w, unsigned char* sA,
+                                             uint64_t* full_a, uint64_t* landed, uint64_t* done, int ai, int lane,
+                                             const CUtensorMap* tm_main, const CUtensorMap* tm_rem) {
+  // my rows of this band: every NAW-th, by global index; the copies of row j + NAW are issued before row j is finished
+  const int j0 = first_mine(2 * w.Pb, ai, NAW);
+  if (j0 < 2 * un.P) k2_issue_row(a, un, j0, 2 * w.Pb + j0, sA, landed, done, lane, tm_main, tm_rem, 2 * NAW);
+  for (int j = j0; j < 2 * un.P; j += NAW) {
+    if (j + NAW < 2 * un.P) k2_issue_row(a, un, j + NAW, 2 * w.Pb + j + NAW, sA, landed, done, lane, tm_main, tm_rem, 2 * NAW);
+    k2_finish_row(a, un, j, 2 * w.Pb + j, sA, landed, full_a, lane);
   }
 }
 
@@ -475,7 +555,9 @@ __device__ __forceinline__ void consume(const Args& a, const Unit& un, const Wal
     const int pg_ = w.Pb + p, jg = 2 * pg_;   // global task / A row index
     mbar_wait(&full_a[jg % (2 * NG)], (jg / (2 * NG)) & 1);
     mbar_wait(&full_a[(jg + 1) % (2 * NG)], ((jg + 1) / (2 * NG)) & 1);
-    const float4* Abase = sA + (size_t)((jg + h) % NG) * AROW;
+    constexpr int NW = Lay<MODE>::NW;
+    const int aslot = (jg + h) % NG;
+    const float4* Abase = sA + (size_t)aslot * (Lay<MODE>::ASTRIDE / 16);
     u64 acc[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -489,12 +571,18 @@ __device__ __forceinline__ void consume(const Args& a, const Unit& un, const Wal
       if (a.dbg & 1) continue;
       const ulonglong2* Wr = reinterpret_cast<const ulonglong2*>(sW + (size_t)(u % NW) * WROW + pg * 65 + 2 * cg);
       const int ey = t - h;  // the two halves use the same window row for different displacements
-      const float4* Ar = (ey >= 0 && ey < ND) ? Abase + ey * ASLICE : sZ;
+      const bool eyv = ey >= 0 && ey < ND;
+      // K1 rows: [ey][ex][px] with the TMA swizzle (key = slot + plane, see a_index).  K2 rows: [ex][dyi = 8 - ey][px] as the
+      // tensor loads deliver them.  A half without a displacement in this step reads the zero slice.
+      const float4* Ar = !eyv ? sZ : (MODE == 0 ? Abase + ey * ASLICE : Abase + (2 * R - ey) * (TW / 4));
+      const int akey = eyv ? aslot + ey * ND : 0;   // zero slice: any permutation will do
+      const int astep = eyv ? ND * TW / 4 : 0;
+      auto aidx = [&](int ex, int grp) { return MODE == 0 ? ex * (TW / 4) + (grp ^ ((akey + ex) & 7)) : ex * astep + grp; };
       float4 a0[ND], a1[ND];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        if (j < ND) a0[j] = Ar[j * 8 + (g0 ^ (j & 7))];
-        if (j >= 4 && j - 4 < ND) a1[j - 4] = Ar[(j - 4) * 8 + (g1 ^ ((j - 4) & 7))];
+        if (j < ND) a0[j] = Ar[aidx(j, g0)];
+        if (j >= 4 && j - 4 < ND) a1[j - 4] = Ar[aidx(j - 4, g1)];
         const ulonglong2 b0 = Wr[j * 8 + (j >> 3)], b1 = Wr[j * 8 + (j >> 3) + 1];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -547,41 +635,32 @@ __device__ __forceinline__ void consume(const Args& a, const Unit& un, const Wal
 }
 
 // ---- K2 scatter warps ----------------------------------------------------------------------------
-// dense_image_warp backward for one staged dwarp row: 8 lanes per pixel (4 channels each), 4 pixels per step
+// dense_image_warp backward for one staged dwarp row: 8 lanes per pixel (4 channels each), 4 pixels per step.
+// Scatter warp (cw, h) drains staging slot 2 cw + h: row 2p + h of every task p of consumer warp cw (one producer, one
+// consumer per slot; `nuse` = rows taken from the slot so far, over all bands).
 template <typename T, typename TF>
 __device__ __forceinline__ void scatter_rows(const Args& a, const Unit& un, const Walk& w, const float4* sS,
-                                             uint64_t* full_d, uint64_t* empty_d, int sw, int lane, int (&nuse)[2]) {
+                                             uint64_t* full_d, uint64_t* empty_d, int cw, int h, int lane, int& nuse) {
   const T* __restrict__ c2 = reinterpret_cast<const T*>(a.c2);
   const TF* __restrict__ flow = reinterpret_cast<const TF*>(a.flow);
   const int psub = lane >> 3, f4 = lane & 7;
-  // rows 2p, 2p+1 of the band's tasks p = pfirst, pfirst + NCW, ... (global index = sw mod NCW) that consumer warp `sw`
-  // stages into its slots 2 sw, 2 sw + 1; nuse[h] = rows taken from slot 2 sw + h so far, over all bands
-  const int pfirst = first_mine(w.Pb, sw, NCW);
-  auto find_row = [&](int& jj) -> bool {  // first jj' >= jj that names a row of the band
-    for (;; ++jj) {
-      const int p = pfirst + NCW * (jj >> 1);
-      if (p >= un.P) return false;
-      if (2 * p + (jj & 1) < un.rows) return true;
-    }
-  };
-  auto load_flow = [&](int jj, TF& f0, TF& f1) {  // flow of this lane's pixel of row jj
-    const int y = un.y0 + 2 * (pfirst + NCW * (jj >> 1)) + (jj & 1);
+  const int slot = 2 * cw + h;
+  auto load_flow = [&](int p, TF& f0, TF& f1) {  // flow of this lane's pixel of row 2p + h
+    const int y = un.y0 + 2 * p + h;
     const int x = min(un.x0 + lane, a.W - 1);
     const size_t pp = ((size_t)un.b * a.H + y) * a.W + x;
     f0 = flow[2 * pp];
     f1 = flow[2 * pp + 1];
   };
-  int jj = 0;
-  bool have = find_row(jj);
+  auto row_ok = [&](int p) { return p < un.P && 2 * p + h < un.rows; };
+  int p = first_mine(w.Pb, cw, NCW);
   TF nf0 = TF(0.f), nf1 = TF(0.f);
-  if (have) load_flow(jj, nf0, nf1);
-  while (have) {
-    const int p = pfirst + NCW * (jj >> 1), h = jj & 1, j = 2 * p + h;
-    const int slot = 2 * sw + h;
-    int jn = jj + 1;
-    const bool have_next = find_row(jn);
-    {  // corners of the rows this warp scatters next (two tasks ahead), assuming moderate flows
-      const int yn = un.y0 + j + 2 * NCW;
+  if (row_ok(p)) load_flow(p, nf0, nf1);
+  for (; row_ok(p); p += NCW) {
+    const int j = 2 * p + h;
+    const bool have_next = row_ok(p + NCW);
+    {  // corners of the row this warp scatters after the next one, assuming moderate flows
+      const int yn = un.y0 + j + 4 * NCW;
       if (yn < a.H) {
         const int xlo = max(un.x0 - 2 * R, 0), xhi = min(un.x0 + TW + 2 * R, a.W);
         prefetch_pixels(c2 + (((size_t)un.b * a.H + yn) * a.W + xlo) * a.C + (size_t)un.cs * KS, xhi - xlo,
@@ -612,9 +691,9 @@ __device__ __forceinline__ void scatter_rows(const Args& a, const Unit& un, cons
         br[k] = ld4(c2 + i_tl + (size_t)a.W * a.C + a.C);
       }
       if (half == 0) {
-        if (have_next) load_flow(jn, nf0, nf1);  // consumed at the top of the next row
-        mbar_wait(&full_d[slot], (h ? nuse[1] : nuse[0]) & 1);
-        if (h) ++nuse[1]; else ++nuse[0];
+        if (have_next) load_flow(p + NCW, nf0, nf1);  // consumed at the top of the next row
+        mbar_wait(&full_d[slot], nuse & 1);
+        ++nuse;
       }
 #pragma unroll
       for (int k = 0; k < NB; ++k) {
@@ -664,26 +743,28 @@ __device__ __forceinline__ void scatter_rows(const Args& a, const Unit& un, cons
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_d[slot]);
-    jj = jn;
-    have = have_next;
   }
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
-// NAW_ = A-producer warps; K1: the other 12 - NAW_ warps gather the warped rows; K2: 4 scatter warps (with a flow) and
-// the rest copy c1 rows
+// Warp roles after the 4 consumers.  K1: NAW_ A builders, the other 12 - NAW_ gather the warped rows.  K2: NAW_ warps
+// fetch the A rows, 8 scatter warps (with a flow: one per staging slot), the rest copy c1 rows into the window ring.
 template <int MODE, bool HAS_FLOW, int NAW_, typename T, typename TF>
-__global__ void __launch_bounds__(NTHREADS, 1) bwd_fused_kernel(const Args a) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  float4* sW = reinterpret_cast<float4*>(smem + OFF_W);
-  float4* sA = reinterpret_cast<float4*>(smem + OFF_A);
-  float4* sZ = reinterpret_cast<float4*>(smem + OFF_Z);
-  float4* sS = reinterpret_cast<float4*>(smem + OFF_S);
-  uint64_t* full_w = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+__global__ void __launch_bounds__(NTHREADS, 1)
+bwd_fused_kernel(const Args a, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap2) {
+  using L = Lay<MODE>;
+  constexpr int NW = L::NW;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  float4* sW = reinterpret_cast<float4*>(smem + L::OFF_W);
+  float4* sA = reinterpret_cast<float4*>(smem + L::OFF_A);
+  float4* sZ = reinterpret_cast<float4*>(smem + L::OFF_Z);
+  float4* sS = reinterpret_cast<float4*>(smem + L::OFF_S);
+  uint64_t* full_w = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
   uint64_t* full_a = full_w + 2 * NW;
   uint64_t* done = full_a + 2 * NG;
   uint64_t* full_d = done + NT;
   uint64_t* empty_d = full_d + NDS;
+  uint64_t* landed = empty_d + NDS;   // K2 only
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -691,9 +772,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_fused_kernel(const Args a) {
     for (int i = 0; i < 2 * NG; ++i) mbar_init(&full_a[i], 32);
     for (int i = 0; i < NT; ++i) mbar_init(&done[i], 1);
     for (int i = 0; i < NDS; ++i) { mbar_init(&full_d[i], 16); mbar_init(&empty_d[i], 1); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (MODE == 1)
+      for (int i = 0; i < 2 * NG; ++i) mbar_init(&landed[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the async (TMA) proxy
   }
   for (int i = tid; i < ASLICE; i += NTHREADS) sZ[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // sZ is a TMA source in K1
   __syncthreads();
 
   // every role walks the CTA's bands in the same order with its own copy of the walk state
@@ -710,38 +794,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_fused_kernel(const Args a) {
     return;
   }
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_OTHER));
-  constexpr int NOTHER = NTHREADS / 32 - NCW - NAW_;
-  if (warp < NCW + NAW_) {
+  constexpr int NHELP = NTHREADS / 32 - NCW;   // 12
+  const int hi = warp - NCW;
+  if constexpr (MODE == 0) {
+    constexpr int NGW = NHELP - NAW_;
+    static_assert(NGW >= 1, "K1 warp split");
     bool pending = false;
     while (w.next(a, un)) {
-      if (MODE == 0) produce_a_k1<NAW_, T>(a, un, w, reinterpret_cast<float*>(sA), full_a, done, warp - NCW, lane, pending);
-      else produce_a_k2<NAW_>(a, un, w, reinterpret_cast<float*>(sA), full_a, done, warp - NCW, lane);
+      if (hi < NAW_)
+        produce_a_k1<NAW_, T>(a, un, w, reinterpret_cast<float*>(sA), full_a, sZ, done, hi, lane, pending, &tmap);
+      else produce_window<HAS_FLOW, NGW, NW, T, TF>(a, un, w, sW, full_w, done, hi - NAW_, lane);
       w.advance(un);
     }
-    // K1: my last bulk stores must have read their shared-memory source before the CTA's memory goes away
-    if (MODE == 0 && pending && lane < ND) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    return;
-  }
-  const int oi = warp - NCW - NAW_;
-  int nuse[2] = {0, 0};
-  while (w.next(a, un)) {
-    if (MODE == 0) {
-      produce_window<HAS_FLOW, NOTHER, T, TF>(a, un, w, sW, full_w, done, oi, lane);
-    } else if (!HAS_FLOW) {
-      produce_window<false, NOTHER, T, TF>(a, un, w, sW, full_w, done, oi, lane);
-    } else if (oi < NOTHER - NCW) {
-      produce_window<false, NOTHER - NCW, T, TF>(a, un, w, sW, full_w, done, oi, lane);
-    } else {
-      scatter_rows<T, TF>(a, un, w, sS, full_d, empty_d, oi - (NOTHER - NCW), lane, nuse);
+    // my last tensor stores must have read their shared-memory source before the CTA's memory goes away
+    if (hi < NAW_ && pending && lane < ND) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  } else {
+    constexpr int NSW = HAS_FLOW ? 2 * NCW : 0;   // one scatter warp per staging slot
+    constexpr int NWW = NHELP - NAW_ - NSW;
+    static_assert(NWW >= 1, "window producers");
+    int nuse = 0;
+    while (w.next(a, un)) {
+      if (hi < NAW_)
+        produce_a_k2<NAW_>(a, un, w, smem + L::OFF_A, full_a, landed, done, hi, lane, &tmap, &tmap2);
+      else if (hi < NAW_ + NWW) produce_window<false, NWW, NW, T, TF>(a, un, w, sW, full_w, done, hi - NAW_, lane);
+      else scatter_rows<T, TF>(a, un, w, sS, full_d, empty_d, (hi - NAW_ - NWW) >> 1, (hi - NAW_ - NWW) & 1, lane, nuse);
+      w.advance(un);
     }
-    w.advance(un);
   }
 }
 
 // Workspace: transposed g' (fp32), then - with a flow - an fp32 dc2 accumulator for 16-bit tensors and an fp32 dflow
 // accumulator when the channels are processed in several slices.
 struct Plan {
-  int nsx, nslices, npair;
+  int nsx, nslices, npair, wpitch;   // wpitch = row pitch of the workspace planes in floats (W rounded up to 4)
   long long Q;   // (image, strip, slice, row pair) units
   int grid;      // persistent CTAs (one per SM: the kernel uses all of an SM's shared memory)
   size_t ws_off, acc_off, dflow_off, total;
@@ -761,7 +846,8 @@ inline Plan make_plan(int B, int H, int W, int C, size_t elt, size_t flow_elt, b
   p.grid = (int)g;
   size_t off = 0;
   p.ws_off = off;
-  off += up256((size_t)B * H * p.nsx * D * TW * 4);
+  p.wpitch = (W + 3) & ~3;
+  off += up256((size_t)B * H * D * p.wpitch * 4);
   p.acc_in_ws = has_flow && elt != 4;
   p.acc_off = off;
   if (p.acc_in_ws) off += up256((size_t)B * H * W * C * 4);

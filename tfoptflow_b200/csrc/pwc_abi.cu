@@ -20,10 +20,10 @@
 #define PWC_BWD_NA1N 8   /* K1 without a flow: 8 A producers + 4 copy warps */
 #endif
 #ifndef PWC_BWD_NA2
-#define PWC_BWD_NA2 6    /* K2 with a flow: 6 A producers + 2 copy + 4 scatter warps */
+#define PWC_BWD_NA2 2    /* K2 with a flow: 2 A-row warps + 2 copy warps + 8 scatter warps (one per staging slot) */
 #endif
 #ifndef PWC_BWD_NA2N
-#define PWC_BWD_NA2N 8   /* K2 without a flow: 8 A producers + 4 copy warps */
+#define PWC_BWD_NA2N 6   /* K2 without a flow: 6 A-row warps + 6 copy warps */
 #endif
 #include "common.cuh"
 #include "fwd_generic.cuh"
@@ -364,6 +364,30 @@ int cv_bwd_typed(const void* g, const void* out, const void* c1, const void* war
   return bwd_corr_launch<1, T, T>(g, out, c1, dwarp, B, H, W, C, r, gps, ops, st, dev);
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (the library links cudart statically and not
+// libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int encode_tensor_map(CUtensorMap* tm, void* base, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box,
+                      const cuuint32_t* estr, CUtensorMapSwizzle swz) {
+  static std::atomic<EncodeTiledFn> fn{nullptr};
+  EncodeTiledFn f = fn.load();
+  if (f == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || p == nullptr ||
+        q != cudaDriverEntryPointSuccess)
+      return fail(PWC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    f = reinterpret_cast<EncodeTiledFn>(p);
+    fn.store(f);
+  }
+  const CUresult r = f(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(PWC_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+  return PWC_OK;
+}
+
 // Fused backward (bwd_fused.cuh): K1 = dc1 + transposed g' workspace, K2 = dwarp -> dc2 / dflow.  Two kernel launches
 // per level (plus a memset of the scatter target, and a cast for 16-bit tensors).
 template <typename T, typename TF>
@@ -382,7 +406,7 @@ int bwd_fused_launch(const void* g, const void* out, const void* c1, const void*
   a.g = g; a.out = out; a.flow = flow; a.c2 = c2;
   a.ws = (float*)(base + pl.ws_off);
   a.B = B; a.H = H; a.W = W; a.C = C;
-  a.nsx = pl.nsx; a.nslices = pl.nslices; a.NPAIR = pl.npair; a.Q = pl.Q;
+  a.nsx = pl.nsx; a.nslices = pl.nslices; a.NPAIR = pl.npair; a.Q = pl.Q; a.wpitch = pl.wpitch;
   a.flow_scale = scale; a.inv_c = 1.0f / (float)C;
   a.dbg = g_bwd_dbg.load();
   if ((long long)B * pl.nsx * pl.nslices >= (1LL << 31)) return fail(PWC_ERR_BAD_SHAPE, "too many strips");
@@ -409,11 +433,23 @@ int bwd_fused_launch(const void* g, const void* out, const void* c1, const void*
       PWC_CUDA(cudaMemsetAsync(dfacc, 0, npix * 2 * 4, st));
     }
   }
+  // the g' workspace as a 4-d tensor [B * H][dyi][dxi][x] (see bwd_fused.cuh): K1 stores 32 px x 9-plane boxes through the
+  // 128-byte swizzle, K2 loads 32 px x 9 dyi boxes (and two 4 px x 3 plane x 9 dyi remainder boxes) at multiples of 4 px
+  CUtensorMap tm_store, tm_main, tm_rem;
+  {
+    const cuuint64_t wp = (cuuint64_t)pl.wpitch;
+    const cuuint64_t dims[4] = {(cuuint64_t)W, 9, 9, (cuuint64_t)B * H};
+    const cuuint64_t strides[3] = {wp * 4, wp * 4 * 9, wp * 4 * 81};
+    const cuuint32_t box_store[4] = {32, 9, 1, 1}, box_main[4] = {32, 1, 9, 1}, box_rem[4] = {4, 3, 9, 1}, estr[4] = {1, 1, 1, 1};
+    if ((rc = encode_tensor_map(&tm_store, a.ws, dims, strides, box_store, estr, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = encode_tensor_map(&tm_main, a.ws, dims, strides, box_main, estr, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
+    if ((rc = encode_tensor_map(&tm_rem, a.ws, dims, strides, box_rem, estr, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
+  }
   a.feat = c2; a.dst = dc1;
-  k1<<<(unsigned)grid, bf::NTHREADS, bf::SMEM_BYTES, st>>>(a);
+  k1<<<(unsigned)grid, bf::NTHREADS, bf::Lay<0>::SMEM_BYTES, st>>>(a, tm_store, tm_store);
   PWC_LAUNCH_CHECK();
   a.feat = c1; a.dst = dc2; a.acc = acc; a.dflow = dflow; a.dflow_acc = dfacc;
-  k2<<<(unsigned)grid, bf::NTHREADS, bf::SMEM_BYTES, st>>>(a);
+  k2<<<(unsigned)grid, bf::NTHREADS, bf::Lay<1>::SMEM_BYTES, st>>>(a, tm_main, tm_rem);
   PWC_LAUNCH_CHECK();
   if (hf && pl.acc_in_ws && (rc = cast_launch<T>(acc, dc2, (int64_t)n, st, dev))) return rc;
   if (hf && dfacc && pl.dflow_in_ws && (rc = cast_launch<TF>(dfacc, dflow, (int64_t)npix * 2, st, dev))) return rc;
