@@ -72,6 +72,9 @@ uint64_t pwc_launch_count(void);
  *   "stream_debug"    DIAGNOSTICS ONLY, default 0: bits 1 / 2 / 4 skip the correlation / the gathers / the stores
  *                     of the streaming kernel (RESULTS ARE WRONG; bench.py refuses to report with them set), bit 8
  *                     forces the LDG path for c1, bit 16 records the event trace read by pwc_debug_read_trace
+ *   "bwd_prefetch"    L2 prefetch distance of the fused backward's producer warps, in turns of their row loops
+ *                     (default 1: two turns ahead re-reads 40 % of the
+ *                     prefetched lines from DRAM, profiles/r02_notes.md; 0 = off, 0..8)
  *   "bwd_debug"       DIAGNOSTICS ONLY, default 0: bits 1 / 2 / 4 / 8 / 16 skip the FMA loop / the g, out (K1) or
  *                     workspace (K2) loads / the window-row loads / the scatter / the workspace stores of the fused
  *                     backward (RESULTS ARE WRONG; bench.py refuses to report with it set) */

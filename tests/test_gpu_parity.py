@@ -391,7 +391,7 @@ def test_non_finite_features_do_not_leak_into_the_zero_padding(dev):
 
 def test_options_round_trip_and_host_path_validation(dev):
     for key, val in (("fwd_impl", 2), ("bwd_impl", 1), ("overlap_levels", 0), ("side_sms", 8), ("side_reverse", 0),
-                     ("tile_small", 0), ("bwd_tiled", 0), ("stream_ctas", 100), ("stream_prefetch", 2), ("stream_debug", 0), ("bwd_debug", 0)):
+                     ("tile_small", 0), ("bwd_tiled", 0), ("stream_ctas", 100), ("stream_prefetch", 2), ("stream_debug", 0), ("bwd_debug", 0), ("bwd_prefetch", 1)):
         old = _ffi.get_option(key)
         _ffi.set_option(key, val)
         assert _ffi.get_option(key) == val

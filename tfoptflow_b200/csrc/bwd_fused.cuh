@@ -89,6 +89,7 @@ struct Args {
   int wpitch;                // row pitch of a workspace plane in floats (W rounded up to 4)
   long long Q;               // B * nsx * nslices * NPAIR (strip, row pair) units, split evenly over the CTAs
   float flow_scale, inv_c;
+  int pf;    // L2 prefetch distance of the producers, in turns of their row loop (option bwd_prefetch; 0 = off)
   int dbg;   // timing experiments only (option bwd_debug): 1 = no FMA loop, 2 = A rows without loads, 4 = window rows
              // without loads, 8 = no scatter (K2), 16 = no workspace stores (K1); results are wrong when non-zero
 };
@@ -291,11 +292,10 @@ __device__ __forceinline__ void produce_window(const Args& a, const Unit& un, co
     if (WARP) prefetch_span(flow + rp * 2, (xhi - xlo) * 2 * (int)sizeof(TF), lane);
   };
   const int u0 = first_mine(w.Ub, pi, NPROD);  // rows are dealt round-robin by GLOBAL index
-  prefetch_row(u0);
-  prefetch_row(u0 + NPROD);
+  for (int k = 0; k < a.pf; ++k) prefetch_row(u0 + k * NPROD);
   for (int u = u0; u < un.U; u += NPROD) {
     const int ug = w.Ub + u;
-    prefetch_row(u + 2 * NPROD);
+    if (a.pf > 0) prefetch_row(u + a.pf * NPROD);
     if (ug >= NW) wait_window_free(done, ug - NW, w, un.P);
     float4* Wd = sW + (size_t)(ug % NW) * WROW;
     const int y = un.y0 - R + u;
@@ -395,11 +395,10 @@ __device__ __forceinline__ void produce_a_k1(const Args& a, const Unit& un, cons
   };
   // `pending` (caller's, lives across bands): bulk stores of my previous row not yet known to have read their source
   const int j0 = first_mine(2 * w.Pb, ai, NAW);
-  prefetch_row(j0);
-  prefetch_row(j0 + NAW);
+  for (int k = 0; k < a.pf; ++k) prefetch_row(j0 + k * NAW);
   for (int j = j0; j < 2 * un.P; j += NAW) {
     const int jg = 2 * w.Pb + j;
-    prefetch_row(j + 2 * NAW);
+    if (a.pf > 0) prefetch_row(j + a.pf * NAW);
     if (jg >= NG) {
       const int p = (jg - NG) >> 1;
       mbar_wait(&done[p % NT], (p / NT) & 1);
@@ -488,7 +487,7 @@ __device__ __forceinline__ void k2_issue_row(const Args& a, const Unit& un, int 
     // ex = 1..3 (c = -4): pixels x0 + 28 .. 31 of planes dxi = 7, 6, 5;  ex = 5..7 (c = 0): x0 + 32 .. 35 of dxi = 3, 2, 1
     tma_load_4d(A + AROW * 16, tm_rem, bar, un.x0 + TW - R, 5, 0, row);
     tma_load_4d(A + AROW * 16 + AREM / 2, tm_rem, bar, un.x0 + TW, 1, 0, row);
-  } else if (lane <= ND && j + pf < un.rows) {
+  } else if (pf > 0 && lane <= ND && j + pf < un.rows) {
     // pull a row further down the band into L2: lanes 1..9 take one main box each (the remainder boxes share its lines)
     const int ex = lane - 1;
     tma_prefetch_4d(tm_main, un.x0 + ((ex - R) & ~3), 2 * R - ex, 0, un.b * a.H + un.y0 + j + pf);
@@ -527,9 +526,9 @@ __device__ __forceinline__ void produce_a_k2(const Args& a, const Unit& un, cons
                                              const CUtensorMap* tm_main, const CUtensorMap* tm_rem) {
   // my rows of this band: every NAW-th, by global index; the copies of row j + NAW are issued before row j is finished
   const int j0 = first_mine(2 * w.Pb, ai, NAW);
-  if (j0 < 2 * un.P) k2_issue_row(a, un, j0, 2 * w.Pb + j0, sA, landed, done, lane, tm_main, tm_rem, 2 * NAW);
+  if (j0 < 2 * un.P) k2_issue_row(a, un, j0, 2 * w.Pb + j0, sA, landed, done, lane, tm_main, tm_rem, a.pf * NAW);
   for (int j = j0; j < 2 * un.P; j += NAW) {
-    if (j + NAW < 2 * un.P) k2_issue_row(a, un, j + NAW, 2 * w.Pb + j + NAW, sA, landed, done, lane, tm_main, tm_rem, 2 * NAW);
+    if (j + NAW < 2 * un.P) k2_issue_row(a, un, j + NAW, 2 * w.Pb + j + NAW, sA, landed, done, lane, tm_main, tm_rem, a.pf * NAW);
     k2_finish_row(a, un, j, 2 * w.Pb + j, sA, landed, full_a, lane);
   }
 }
@@ -660,8 +659,8 @@ __device__ __forceinline__ void scatter_rows(const Args& a, const Unit& un, cons
     const int j = 2 * p + h;
     const bool have_next = row_ok(p + NCW);
     {  // corners of the row this warp scatters after the next one, assuming moderate flows
-      const int yn = un.y0 + j + 4 * NCW;
-      if (yn < a.H) {
+      const int yn = un.y0 + j + 2 * a.pf * NCW;
+      if (a.pf > 0 && yn < a.H) {
         const int xlo = max(un.x0 - 2 * R, 0), xhi = min(un.x0 + TW + 2 * R, a.W);
         prefetch_pixels(c2 + (((size_t)un.b * a.H + yn) * a.W + xlo) * a.C + (size_t)un.cs * KS, xhi - xlo,
                         (size_t)a.C * sizeof(T), lane);

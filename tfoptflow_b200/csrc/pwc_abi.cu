@@ -14,7 +14,7 @@
 #include "bwd.cuh"
 #include "bwd_fused.cuh"
 #ifndef PWC_BWD_NA1
-#define PWC_BWD_NA1 6    /* K1 with a flow: 6 A producers + 6 gather warps */
+#define PWC_BWD_NA1 5    /* K1 with a flow: 5 A builders + 7 gather warps (6 + 6: 592 us on level 2, 5 + 7: 583, 7 + 5: 600) */
 #endif
 #ifndef PWC_BWD_NA1N
 #define PWC_BWD_NA1N 8   /* K1 without a flow: 8 A producers + 4 copy warps */
@@ -41,6 +41,7 @@ std::atomic<int> g_fwd_impl{0};
 std::atomic<int> g_stream_ctas{0};
 std::atomic<int> g_stream_pf{4};
 std::atomic<int> g_stream_dbg{0};
+std::atomic<int> g_bwd_pf{1};    // fused backward: L2 prefetch distance of the producers (turns of their row loop)
 std::atomic<int> g_bwd_dbg{0};   // fused backward: timing experiments only (see bwd_fused.cuh Args::dbg)
 // levels at least this tall take the streaming kernel (it pays ~5 warm-up slabs per strip segment): measured
 // 28 rows 84 us streaming vs 91 us tiled, 14 rows 56 vs 46 us
@@ -409,6 +410,7 @@ int bwd_fused_launch(const void* g, const void* out, const void* c1, const void*
   a.nsx = pl.nsx; a.nslices = pl.nslices; a.NPAIR = pl.npair; a.Q = pl.Q; a.wpitch = pl.wpitch;
   a.flow_scale = scale; a.inv_c = 1.0f / (float)C;
   a.dbg = g_bwd_dbg.load();
+  a.pf = g_bwd_pf.load();
   if ((long long)B * pl.nsx * pl.nslices >= (1LL << 31)) return fail(PWC_ERR_BAD_SHAPE, "too many strips");
   const int grid = pl.grid;  // persistent: one CTA per SM walks its share of the (strip, row pair) units
   auto prep = [&](auto kern) -> int {
@@ -423,15 +425,14 @@ int bwd_fused_launch(const void* g, const void* out, const void* c1, const void*
   int rc = prep(k1);
   if (rc) return rc;
   if ((rc = prep(k2))) return rc;
+  // the scatter targets of K2 (red.global.add) are zeroed between the two kernels, not before K1: the zeros are then
+  // still in L2 when the atomics arrive (before K1 they were evicted by its 1.2 GB of traffic and every atomic paid a
+  // DRAM read)
   float* acc = nullptr;
   float* dfacc = nullptr;
   if (hf) {
     acc = pl.acc_in_ws ? (float*)(base + pl.acc_off) : (float*)dc2;
-    PWC_CUDA(cudaMemsetAsync(acc, 0, n * 4, st));
-    if (pl.nslices > 1) {
-      dfacc = pl.dflow_in_ws ? (float*)(base + pl.dflow_off) : (float*)dflow;
-      PWC_CUDA(cudaMemsetAsync(dfacc, 0, npix * 2 * 4, st));
-    }
+    if (pl.nslices > 1) dfacc = pl.dflow_in_ws ? (float*)(base + pl.dflow_off) : (float*)dflow;
   }
   // the g' workspace as a 4-d tensor [B * H][dyi][dxi][x] (see bwd_fused.cuh): K1 stores 32 px x 9-plane boxes through the
   // 128-byte swizzle, K2 loads 32 px x 9 dyi boxes (and two 4 px x 3 plane x 9 dyi remainder boxes) at multiples of 4 px
@@ -448,6 +449,8 @@ int bwd_fused_launch(const void* g, const void* out, const void* c1, const void*
   a.feat = c2; a.dst = dc1;
   k1<<<(unsigned)grid, bf::NTHREADS, bf::Lay<0>::SMEM_BYTES, st>>>(a, tm_store, tm_store);
   PWC_LAUNCH_CHECK();
+  if (acc) PWC_CUDA(cudaMemsetAsync(acc, 0, n * 4, st));
+  if (dfacc) PWC_CUDA(cudaMemsetAsync(dfacc, 0, npix * 2 * 4, st));
   a.feat = c1; a.dst = dc2; a.acc = acc; a.dflow = dflow; a.dflow_acc = dfacc;
   k2<<<(unsigned)grid, bf::NTHREADS, bf::Lay<1>::SMEM_BYTES, st>>>(a, tm_main, tm_rem);
   PWC_LAUNCH_CHECK();
@@ -563,6 +566,11 @@ int pwc_set_option(const char* key, int value) {
     g_stream_dbg.store(value);
     return PWC_OK;
   }
+  if (!strcmp(key, "bwd_prefetch")) {
+    if (value < 0 || value > 8) return fail(PWC_ERR_BAD_ARG, "bwd_prefetch must be 0..8");
+    g_bwd_pf.store(value);
+    return PWC_OK;
+  }
   if (!strcmp(key, "bwd_debug")) {  // timing experiments only; results are wrong when non-zero
     g_bwd_dbg.store(value);
     return PWC_OK;
@@ -589,6 +597,7 @@ int pwc_get_option(const char* key, int* value) {
   if (!strcmp(key, "stream_prefetch")) { *value = g_stream_pf.load(); return PWC_OK; }
   if (!strcmp(key, "stream_debug")) { *value = g_stream_dbg.load(); return PWC_OK; }
   if (!strcmp(key, "bwd_debug")) { *value = g_bwd_dbg.load(); return PWC_OK; }
+  if (!strcmp(key, "bwd_prefetch")) { *value = g_bwd_pf.load(); return PWC_OK; }
   if (!strcmp(key, "overlap_levels")) { *value = g_overlap.load(); return PWC_OK; }
   if (!strcmp(key, "bwd_impl")) { *value = g_bwd_impl.load(); return PWC_OK; }
   if (!strcmp(key, "side_sms")) { *value = g_side_sms.load(); return PWC_OK; }
