@@ -29,6 +29,9 @@
 #include <cuda.h>   // CUtensorMap (types only: the encode entry point is fetched through the runtime)
 #include "common.cuh"
 
+#ifndef PWC_BWD_GATHER_DEPTH
+#define PWC_BWD_GATHER_DEPTH 2   /* K1 gather: steps (4 corner loads each) in flight ahead of the one being blended */
+#endif
 #ifndef PWC_BWD_LANEMAP
 #define PWC_BWD_LANEMAP 1   /* 0: (cg, pg, h) lane order of the first version */
 #endif
@@ -272,7 +275,7 @@ __device__ __forceinline__ int first_mine(int base, int me, int n) { return ((me
 // ---- B producers -------------------------------------------------------------------------------
 // window row u <-> image row y0 - 4 + u, pixels x0 - 4 .. x0 + 35, channels [32 cs, 32 cs + 32); zero outside the image.
 // 8 lanes per pixel (one float4 each), 4 pixels per step, 10 steps per row.  The flow of all 10 steps is loaded and
-// turned into corner indices / weights first (one latency exposure), then the corners are gathered GB steps at a time.
+// turned into corner indices / weights first (one latency exposure), then the corners are gathered in a software pipeline.
 template <bool WARP, int NPROD, int NW, typename T, typename TF>
 __device__ __forceinline__ void produce_window(const Args& a, const Unit& un, const Walk& w, float4* sW,
                                                uint64_t* full_w, uint64_t* done, int pi, int lane) {
@@ -281,7 +284,6 @@ __device__ __forceinline__ void produce_window(const Args& a, const Unit& un, co
   const int psub = lane >> 3, f4 = lane & 7;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
   constexpr int NIT = WPX / 4;           // 10
-  constexpr int GB = WARP ? 2 : 10;      // steps per gather batch (8 / 10 LDG.128 in flight per lane)
   const T* base = feat + (size_t)un.cs * KS + 4 * f4;
   auto prefetch_row = [&](int u) {
     const int y = un.y0 - R + u;
@@ -331,12 +333,17 @@ __device__ __forceinline__ void produce_window(const Args& a, const Unit& un, co
           }
         }
       }
+      // software pipeline over the 10 steps of the row: the corner loads of step i + GD are issued before step i is
+      // blended, so a lane keeps 4 GD .. 4 (GD + 1) LDG.128 in flight for the whole row instead of one latency exposure
+      // per batch (fully unrolled; the ring of corner registers is indexed at compile time).  Plain copies (K2) issue
+      // the whole row at once.
+      constexpr int GD = WARP ? PWC_BWD_GATHER_DEPTH : NIT - 1;
+      float4 tl[GD + 1], tr[GD + 1], bl[GD + 1], br[GD + 1];
 #pragma unroll
-      for (int it0 = 0; it0 < NIT; it0 += GB) {
-        float4 tl[GB], tr[GB], bl[GB], br[GB];
-#pragma unroll
-        for (int k = 0; k < GB; ++k) {
-          const T* q = base + (size_t)pix[it0 + k] * a.C;
+      for (int i = 0; i < NIT + GD; ++i) {
+        if (i < NIT) {
+          const int k = i % (GD + 1);
+          const T* q = base + (size_t)pix[i] * a.C;
           tl[k] = ld4(q);
           if (WARP) {
             tr[k] = ld4(q + a.C);
@@ -344,9 +351,8 @@ __device__ __forceinline__ void produce_window(const Args& a, const Unit& un, co
             br[k] = ld4(q + (size_t)a.W * a.C + a.C);
           }
         }
-#pragma unroll
-        for (int k = 0; k < GB; ++k) {
-          const int it = it0 + k, px = it * 4 + psub;
+        if (i >= GD) {
+          const int it = i - GD, k = it % (GD + 1), px = it * 4 + psub;
           float4 v = tl[k];
           if (WARP) {
             if (ElemTraits<T>::kIsHalf) {

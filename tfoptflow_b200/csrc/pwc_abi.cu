@@ -14,7 +14,7 @@
 #include "bwd.cuh"
 #include "bwd_fused.cuh"
 #ifndef PWC_BWD_NA1
-#define PWC_BWD_NA1 5    /* K1 with a flow: 5 A builders + 7 gather warps (6 + 6: 592 us on level 2, 5 + 7: 583, 7 + 5: 600) */
+#define PWC_BWD_NA1 4    /* K1 with a flow: 4 A builders + 8 gather warps (level 2: 6 + 6 592 us, 5 + 7 583, 4 + 8 569, 7 + 5 600) */
 #endif
 #ifndef PWC_BWD_NA1N
 #define PWC_BWD_NA1N 8   /* K1 without a flow: 8 A producers + 4 copy warps */
