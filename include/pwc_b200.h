@@ -58,11 +58,14 @@ uint64_t pwc_launch_count(void);
 
 /* Tuning / debug options (process-wide).  pwc_set_option returns PWC_ERR_BAD_ARG for an unknown key or an out-of-range
  * value; pwc_get_option reads back every key pwc_set_option accepts.
- *   "fwd_impl"        0 = auto (default), 1 = generic scalar kernel, 2 = tiled kernel, 3 = streaming kernel,
+ *   "fwd_impl"        0 = auto (default: streaming kernel for r == 4 and H >= 28 - the band GEMM instead for 16-bit
+ *                     features with C in {32, 64} - tiled kernel for short levels and r == 8, generic otherwise),
+ *                     1 = generic scalar kernel, 2 = tiled kernel, 3 = streaming kernel,
  *                     4 = tensor-core band GEMM for 16-bit features (r == 4, C in {32, 64}; other shapes fall back)
  *   "bwd_impl"        0 = auto (default: fused K1/K2 kernels for r == 4, C % 32 == 0, dense g / out; else v1),
  *                     1 = unfused v1 kernels, 2 = fused kernels or PWC_ERR_BAD_ARG when the shape is not covered
- *   "overlap_levels"  1 (default) = pwc_pyramid_fwd forks the short levels onto side streams, 0 = one stream
+ *   "overlap_levels"  1 (default) = pwc_pyramid_fwd forks the short levels onto side streams, 2 = the tall levels after
+ *                     the first get streams of their own as well, 0 = one stream
  *   "side_sms"        SMs the tall levels' persistent kernels leave free for those short levels (default 16, 0..64)
  *   "side_reverse"    1 (default) = fork the short levels largest first
  *   "tile_small"      1 (default) = 8x16 tiles for levels with fewer 8x32 tiles than SMs

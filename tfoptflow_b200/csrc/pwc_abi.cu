@@ -140,6 +140,11 @@ int fwd_typed(const void* c1, const void* c2, const void* flow, float flow_scale
   // auto: the streaming kernel wins on tall levels (it pays ~5 warm-up slabs per strip segment), the tiled kernel
   // on short ones; measured crossover between H = 28 and H = 56 (profiles/r01_notes.md)
   if (impl == 0) impl = !tuned_ok ? 1 : (r == 4 && H >= kTallMinH ? 3 : 2);
+  // 16-bit features, C = 32 / 64: the tensor-core band GEMM beats the widening CUDA-core loop on tall levels (level 2
+  // fp16: 216 vs 277 us, level 3: 147 vs 160 us; same error against the fp16-regime oracle); shapes it does not cover
+  // fall back to the choice above
+  const int impl_fallback = impl;
+  if (g_fwd_impl.load() == 0 && sizeof(T) == 2 && tuned_ok && r == 4 && (C == 32 || C == 64) && H >= kTallMinH) impl = 4;
   if (impl == 3 && r != 4) impl = 2;  // the streaming kernel is written for search_range 4
   // un-warped small level (the pyramid top): too few tiles for the tiled kernel, one thread per output element wins
   if (g_fwd_impl.load() == 0 && flow == nullptr && vec_ok && (int64_t)B * H * W <= 16384) {
@@ -163,7 +168,7 @@ int fwd_typed(const void* c1, const void* c2, const void* flow, float flow_scale
       if (r == 4) rc = pwc::mma16::launch<T, TF>((const T*)c1, (const T*)c2, (const TF*)flow, flow_scale, (T*)out, B, H, W, C, ops, st);
     if (rc == 0) { PWC_LAUNCH_CHECK(); return PWC_OK; }
     if (rc < 0) return fail(PWC_ERR_CUDA, "mma16 kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-    impl = r == 4 && H >= kTallMinH ? 3 : 2;  // shape not covered
+    impl = g_fwd_impl.load() == 0 ? impl_fallback : (r == 4 && H >= kTallMinH ? 3 : 2);  // shape not covered
   }
 #ifdef PWC_HAVE_STREAM_KERNEL
   if (impl == 3) {
@@ -628,8 +633,8 @@ int pwc_warp_cost_volume_fwd(const void* c1, const void* c2, const void* flow, f
 // cuda_stream still sees "all levels done" as one unit of stream-ordered work.
 namespace {
 struct SideStreams {
-  cudaStream_t s[3] = {nullptr, nullptr, nullptr};
-  cudaEvent_t fork = nullptr, join[3] = {nullptr, nullptr, nullptr};
+  cudaStream_t s[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // 0-2: short levels, 3-5: tall levels after the first
+  cudaEvent_t fork = nullptr, join[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool ok = false;
 };
 SideStreams* side_streams_for_device() {
@@ -638,7 +643,7 @@ SideStreams* side_streams_for_device() {
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   SideStreams& S = per_dev[dev];
   if (!S.ok) {
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < 6; ++i) {
       if (cudaStreamCreateWithFlags(&S.s[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
       if (cudaEventCreateWithFlags(&S.join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
     }
@@ -665,7 +670,7 @@ int pwc_pyramid_fwd(const pwc_level_t* levels, int n_levels, int B, int r, int d
   cudaStream_t main_st = (cudaStream_t)cuda_stream;
   SideStreams* S = (n_levels > 1 && g_overlap.load()) ? side_streams_for_device() : nullptr;
   int n_side = 0, rc = PWC_OK;
-  bool used[3] = {false, false, false};
+  bool used[6] = {false, false, false, false, false, false};
   // The short levels are latency-bound (few CTAs each) and the tall levels' persistent kernels would otherwise own
   // every SM: the tall kernels leave `side_sms` SMs free, the first of them is launched (its CTAs are placed at once),
   // then the short levels are forked onto side streams - they can only land on the free SMs and run there NEXT TO
@@ -691,19 +696,33 @@ int pwc_pyramid_fwd(const pwc_level_t* levels, int n_levels, int B, int r, int d
                      L.out_pixel_stride, S->s[k]);
     }
   };
+  // overlap_levels 2: the tall levels after the first go to streams of their own as well - they are independent too, and
+  // the CTAs of the next persistent kernel then start on the SMs the previous one's early finishers leave, instead of
+  // after its last CTA
+  int n_tall = 0;
   for (int i = 0; i < n_levels && rc == PWC_OK; ++i) {
     const pwc_level_t& L = levels[i];
     if (S && L.H < kTallMinH) continue;
+    cudaStream_t st = main_st;
+    if (S && g_overlap.load() >= 2 && n_tall > 0) {
+      const int k = 3 + (n_tall - 1) % 3;
+      if (!used[k]) {
+        if (cudaStreamWaitEvent(S->s[k], S->fork, 0) != cudaSuccess) { rc = fail(PWC_ERR_CUDA, "cudaStreamWaitEvent failed"); break; }
+        used[k] = true;
+      }
+      st = S->s[k];
+    }
+    ++n_tall;
     t_reserve_sms = reserve;
     rc = fwd_entry(L.c1, L.c2, L.flow, L.flow_scale, L.out, B, L.H, L.W, L.C, r, dtype, flow_dtype,
-                   L.out_pixel_stride, main_st);
+                   L.out_pixel_stride, st);
     t_reserve_sms = 0;
     if (S && !forked && rc == PWC_OK) fork_short();
   }
   if (S && !forked && rc == PWC_OK) fork_short();  // no tall level at all
   // join whatever was forked, also on the error path: the caller's stream must not be left racing side-stream work
   if (S)
-    for (int k = 0; k < 3; ++k)
+    for (int k = 0; k < 6; ++k)
       if (used[k]) {
         if (cudaEventRecord(S->join[k], S->s[k]) != cudaSuccess || cudaStreamWaitEvent(main_st, S->join[k], 0) != cudaSuccess)
           if (rc == PWC_OK) rc = fail(PWC_ERR_CUDA, "joining a side stream failed");
