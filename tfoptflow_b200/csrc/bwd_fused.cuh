@@ -32,6 +32,9 @@
 #ifndef PWC_BWD_GATHER_DEPTH
 #define PWC_BWD_GATHER_DEPTH 2   /* K1 gather: steps (4 corner loads each) in flight ahead of the one being blended */
 #endif
+#ifndef PWC_BWD_SCATTER_NB
+#define PWC_BWD_SCATTER_NB 2   /* K2 scatter: 2 = corners a quarter row at a time (8 LDG.128 in flight), 4 = half a row */
+#endif
 #ifndef PWC_BWD_LANEMAP
 #define PWC_BWD_LANEMAP 1   /* 0: (cg, pg, h) lane order of the first version */
 #endif
@@ -678,9 +681,9 @@ __device__ __forceinline__ void scatter_rows(const Args& a, const Unit& un, cons
     const int y = un.y0 + j;
     const SampleCoord sc = sample_coord_v<T, TF>(nf0, nf1, a.flow_scale, un.b, y, min(un.x0 + lane, a.W - 1), a.H, a.W);
     const float4* S = sS + (size_t)slot * SROW;
+    constexpr int NB = PWC_BWD_SCATTER_NB;  // steps (4 pixels each) per batch of corner loads
 #pragma unroll 1
-    for (int half = 0; half < 4; ++half) {
-      constexpr int NB = TW / 16;  // steps per quarter row
+    for (int half = 0; half < TW / 4 / NB; ++half) {
       float4 tl[NB], tr[NB], bl[NB], br[NB];
       int pixs[NB];
 #pragma unroll
