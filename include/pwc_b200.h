@@ -62,7 +62,7 @@ uint64_t pwc_launch_count(void);
  *                     features with C in {32, 64} - tiled kernel for short levels and r == 8, generic otherwise),
  *                     1 = generic scalar kernel, 2 = tiled kernel, 3 = streaming kernel,
  *                     4 = tensor-core band GEMM for 16-bit features (r == 4, C in {32, 64}; other shapes fall back)
- *   "bwd_impl"        0 = auto (default: fused K1/K2 kernels for r == 4, C % 32 == 0, dense g / out; else v1),
+ *   "bwd_impl"        0 = auto (default: fused K1/K2 kernels for r == 4, C % 4 == 0 (16-bit: C % 8), dense g / out; else v1),
  *                     1 = unfused v1 kernels, 2 = fused kernels or PWC_ERR_BAD_ARG when the shape is not covered
  *   "overlap_levels"  1 (default) = pwc_pyramid_fwd forks the short levels onto side streams, 2 = the tall levels after
  *                     the first get streams of their own as well, 0 = one stream

@@ -22,3 +22,5 @@ for impl in (1, 2):
         e = np.abs(got.cpu().numpy() - want)
         rms = np.sqrt(np.mean(want.astype(np.float64) ** 2))
         print(f"impl {impl} {name}: max err {e.max():.3e} ({e.max() / rms:.2e} x rms) at {np.unravel_index(e.argmax(), e.shape)}", flush=True)
+        if not e.max() <= 2e-5 * rms:
+            raise SystemExit(f"impl {impl} {name}: error above 2e-5 x rms")

@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
 IMPLS = [1, 2, 3]  # generic, tiled, streaming (3 falls back to 2 where it does not apply)
-BWD_IMPLS = [1, 0]  # unfused v1 kernels, auto (fused K1/K2 kernels where they apply: r = 4, C % 32 == 0)
+BWD_IMPLS = [1, 0]  # unfused v1 kernels, auto (fused K1/K2 kernels where they apply: r = 4, C % 4 == 0, 16-bit C % 8 == 0)
 
 
 @pytest.fixture(scope="module")

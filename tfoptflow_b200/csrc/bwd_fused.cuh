@@ -201,12 +201,14 @@ __device__ __forceinline__ float ld1<__nv_bfloat16>(const __nv_bfloat16* p) {
 }
 
 // 8 consecutive channels -> global, in the tensor dtype
-__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
-  st4(p, make_float4(v[0], v[1], v[2], v[3]));
-  st4(p + 4, make_float4(v[4], v[5], v[6], v[7]));
+// (n = channels of the 8 that exist: a partial last slice has a multiple of 4 (fp32) / 8 (16-bit) of them)
+__device__ __forceinline__ void st8(float* p, const float (&v)[8], int n) {
+  if (n >= 4) st4(p, make_float4(v[0], v[1], v[2], v[3]));
+  if (n >= 8) st4(p + 4, make_float4(v[4], v[5], v[6], v[7]));
 }
 template <typename T>
-__device__ __forceinline__ void st8(T* p, const float (&v)[8]) {  // 16-bit: one 16-byte store
+__device__ __forceinline__ void st8(T* p, const float (&v)[8], int n) {  // 16-bit: one 16-byte store
+  if (n < 8) return;
   uint4 u;
   uint32_t* w = reinterpret_cast<uint32_t*>(&u);
 #pragma unroll
@@ -220,6 +222,7 @@ __device__ __forceinline__ void st8(T* p, const float (&v)[8]) {  // 16-bit: one
 
 struct Unit {
   int b, x0, y0, rows, P, U, cs, sx;   // rows = valid rows of the band, P = row pairs, U = window rows
+  int cv;                              // valid channels of slice cs: 32, less in the last slice when C % 32 != 0
 };
 
 // The kernel is persistent: CTA i owns the units [Q i / G, Q (i + 1) / G) of the linearised (image, strip, slice, row pair)
@@ -243,6 +246,7 @@ struct Walk {
     const int n = (long long)(a.NPAIR - p0) < rem ? a.NPAIR - p0 : (int)rem;
     int id = (int)strip;
     un.cs = id % a.nslices; id /= a.nslices;
+    un.cv = min(KS, a.C - un.cs * KS);
     un.sx = id % a.nsx;
     un.b = id / a.nsx;
     un.x0 = un.sx * TW;
@@ -288,6 +292,7 @@ __device__ __forceinline__ void produce_window(const Args& a, const Unit& un, co
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
   constexpr int NIT = WPX / 4;           // 10
   const T* base = feat + (size_t)un.cs * KS + 4 * f4;
+  const bool cok = 4 * f4 < un.cv;
   auto prefetch_row = [&](int u) {
     const int y = un.y0 - R + u;
     if (u >= un.U || y < 0 || y >= a.H) return;
@@ -347,11 +352,14 @@ __device__ __forceinline__ void produce_window(const Args& a, const Unit& un, co
         if (i < NIT) {
           const int k = i % (GD + 1);
           const T* q = base + (size_t)pix[i] * a.C;
-          tl[k] = ld4(q);
-          if (WARP) {
-            tr[k] = ld4(q + a.C);
-            bl[k] = ld4(q + (size_t)a.W * a.C);
-            br[k] = ld4(q + (size_t)a.W * a.C + a.C);
+          tl[k] = tr[k] = bl[k] = br[k] = zero;
+          if (cok) {   // channels past C in a partial last slice read as zeros
+            tl[k] = ld4(q);
+            if (WARP) {
+              tr[k] = ld4(q + a.C);
+              bl[k] = ld4(q + (size_t)a.W * a.C);
+              br[k] = ld4(q + (size_t)a.W * a.C + a.C);
+            }
           }
         }
         if (i >= GD) {
@@ -633,7 +641,7 @@ __device__ __forceinline__ void consume(const Args& a, const Unit& un, const Wal
         if (un.x0 + 8 * pg + i < a.W) {
           const float2 v0 = unpack2(acc[i][0]), v1 = unpack2(acc[i][1]), v2 = unpack2(acc[i][2]), v3 = unpack2(acc[i][3]);
           const float v[8] = {v0.x, v0.y, v1.x, v1.y, v2.x, v2.y, v3.x, v3.y};
-          st8(dst + (size_t)i * a.C, v);
+          st8(dst + (size_t)i * a.C, v, un.cv - 8 * cg);
         }
       }
     }
@@ -692,7 +700,7 @@ __device__ __forceinline__ void scatter_rows(const Args& a, const Unit& un, cons
         pixs[k] = __shfl_sync(0xffffffffu, sc.pix, px);
         const size_t i_tl = (size_t)pixs[k] * a.C + un.cs * KS + 4 * f4;
         // always a valid address: the coordinates of columns past the image edge were taken at the clamped column
-        if (a.dbg & 8) { tl[k] = tr[k] = bl[k] = br[k] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
+        if ((a.dbg & 8) || 4 * f4 >= un.cv) { tl[k] = tr[k] = bl[k] = br[k] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
         tl[k] = ld4(c2 + i_tl);
         tr[k] = ld4(c2 + i_tl + a.C);
         bl[k] = ld4(c2 + i_tl + (size_t)a.W * a.C);
@@ -707,10 +715,11 @@ __device__ __forceinline__ void scatter_rows(const Args& a, const Unit& un, cons
       for (int k = 0; k < NB; ++k) {
         const int px = (half * NB + k) * 4 + psub, x = un.x0 + px;
         const bool valid = x < a.W && !(a.dbg & 8);
+        const bool cok = 4 * f4 < un.cv;   // lanes of channels past C add nothing
         const float ax = __shfl_sync(0xffffffffu, sc.ax, px), ay = __shfl_sync(0xffffffffu, sc.ay, px);
         const float mx = __shfl_sync(0xffffffffu, sc.mx, px), my = __shfl_sync(0xffffffffu, sc.my, px);
         float dax = 0.f, day = 0.f;
-        if (valid) {
+        if (valid && cok) {
           const size_t i_tl = (size_t)pixs[k] * a.C + un.cs * KS + 4 * f4, i_tr = i_tl + a.C;
           const size_t i_bl = i_tl + (size_t)a.W * a.C, i_br = i_bl + a.C;
           const float4 gw = S[px * 8 + (px >> 3) + f4];
@@ -845,7 +854,7 @@ inline size_t up256(size_t n) { return (n + 255) & ~size_t(255); }
 inline Plan make_plan(int B, int H, int W, int C, size_t elt, size_t flow_elt, bool has_flow, int sms) {
   Plan p{};
   p.nsx = (W + TW - 1) / TW;
-  p.nslices = C / KS;
+  p.nslices = (C + KS - 1) / KS;
   p.npair = (H + 1) / 2;
   p.Q = (long long)B * p.nsx * p.nslices * p.npair;
   // a band shorter than ~4 row pairs pays more for its 8 halo rows than for its own: no more CTAs than that allows
@@ -868,9 +877,9 @@ inline Plan make_plan(int B, int H, int W, int C, size_t elt, size_t flow_elt, b
 
 inline bool covered(int C, int r, int64_t gps, int64_t ops, const void* c1, const void* c2, const void* dc1,
                     const void* dc2, size_t elt) {
-  (void)elt;
   auto al = [&](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
-  return r == R && C % KS == 0 && gps == D && ops == D && al(c1) && al(c2) && al(dc1) && al(dc2);
+  // channels in slices of 32; the last slice may be partial as long as 16-byte vectors never straddle the end of a pixel
+  return r == R && C % (elt == 4 ? 4 : 8) == 0 && gps == D && ops == D && al(c1) && al(c2) && al(dc1) && al(dc2);
 }
 
 }  // namespace bwdf

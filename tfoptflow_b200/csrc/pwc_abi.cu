@@ -472,8 +472,9 @@ int fused_bwd_typed(const void* g, const void* out, const void* c1, const void* 
     const int impl = g_bwd_impl.load();
     const bool ok = pwc::bwdf::covered(C, r, gps, ops, c1, c2, dc1, dc2, sizeof(T));
     if (impl == 2 && !ok)
-      return fail(PWC_ERR_BAD_ARG, "bwd_impl=2: the fused backward needs r == 4, C %% 32 == 0, dense g / out and 16-byte aligned tensors");
-    if (impl != 1 && ok)
+      return fail(PWC_ERR_BAD_ARG, "bwd_impl=2: the fused backward needs r == 4, C %% 4 == 0 (C %% 8 for 16-bit tensors), dense g / out and 16-byte aligned tensors");
+    // auto: below ~1 K pixels the two persistent kernels' set-up costs more than the unfused launches (8x6x8x196: 38 vs 34 us)
+    if (impl != 1 && ok && (impl == 2 || (int64_t)B * H * W >= 1024))
       return bwd_fused_launch<T, TF>(g, out, c1, c2, flow, scale, dc1, dc2, dflow, B, H, W, C, ws, ws_bytes, st, dev);
   }
   if (flow == nullptr) return cv_bwd_typed<T>(g, out, c1, c2, dc1, dc2, B, H, W, C, r, gps, ops, st, dev);
@@ -893,7 +894,7 @@ size_t pwc_bwd_workspace_bytes(int B, int H, int W, int C, int r, int dtype, int
   if (B < 0 || H < 0 || W < 0 || C < 0) return 0;
   // covers both the fused backward and the standalone warp backward (which needs only the fp32 accumulator)
   size_t need = bwd_ws_layout(B, H, W, C, dtype, has_flow != 0).total;
-  if (r == pwc::bwdf::R && C % pwc::bwdf::KS == 0 && B > 0 && H > 0 && W > 0) {
+  if (r == pwc::bwdf::R && C % (elt_size(dtype) == 4 ? 4 : 8) == 0 && C > 0 && B > 0 && H > 0 && W > 0) {
     // flow dtype unknown here: assume a 16-bit flow (the larger layout)
     const size_t f = pwc::bwdf::make_plan(B, H, W, C, elt_size(dtype), 2, has_flow != 0, 148).total;
     if (f > need) need = f;
