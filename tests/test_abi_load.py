@@ -47,9 +47,16 @@ def test_argument_validation_without_gpu(lib):
     assert lib.pwc_cost_volume_fwd(None, None, None, 1, 4, 4, 4, 4, 0, 0, None) == -1  # null pointers
     assert lib.pwc_set_option(b"no_such_option", 1) == -1
     assert lib.pwc_set_option(b"fwd_impl", 9) == -1
-    assert lib.pwc_bwd_workspace_bytes(2, 8, 8, 16, 4, 0, 1) == 2 * (2 * 8 * 8 * 16 * 4)
-    assert lib.pwc_bwd_workspace_bytes(2, 8, 8, 16, 4, 1, 1) == 2 * 8 * 8 * 16 * (2 + 4 + 4)
-    assert lib.pwc_bwd_workspace_bytes(2, 8, 8, 16, 4, 0, 0) == 0
+    # shapes only the unfused kernels take (r != 4): the re-materialised warp + the fp32 dwarp accumulator
+    assert lib.pwc_bwd_workspace_bytes(2, 8, 8, 16, 3, 0, 1) == 2 * (2 * 8 * 8 * 16 * 4)
+    assert lib.pwc_bwd_workspace_bytes(2, 8, 8, 16, 3, 1, 1) == 2 * 8 * 8 * 16 * (2 + 4 + 4)
+    assert lib.pwc_bwd_workspace_bytes(2, 8, 8, 16, 3, 0, 0) == 0
+    # shapes the fused kernels cover (r == 4, C % 4 == 0): the g' tensor [B * H][81][W] fp32, plus an fp32 dc2
+    # accumulator for 16-bit tensors
+    gp = 2 * 8 * 81 * 8 * 4
+    assert lib.pwc_bwd_workspace_bytes(2, 8, 8, 16, 4, 0, 1) == gp
+    assert lib.pwc_bwd_workspace_bytes(2, 8, 8, 16, 4, 0, 0) == gp
+    assert lib.pwc_bwd_workspace_bytes(2, 8, 8, 16, 4, 1, 1) == gp + 2 * 8 * 8 * 16 * 4
 
 
 def test_no_cpu_fallback(lib):
