@@ -227,6 +227,171 @@ fwd_mma16_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* _
   }
 }
 
+// ---- search_range 8 (BASELINE configs[4]: 289 channels), C in {32, 64} -------------------------------------------------
+// Same band GEMM, 32 neighbours per 16-pixel block (17 of 32 diagonals used).  The +-8 halo makes small tiles
+// expensive (an 8 x 32 tile would gather 4.5 halo pixels per output pixel), so the CTA keeps the warped halo of a
+// 16 x 32 tile resident (32 x 48 pixels, 120 KB) and there is no tile-wide staging buffer: each warp stages one
+// (row, 16-pixel block) unit - 16 pixels x 289 channels = 9 248 contiguous bytes of the output - in its own 9 KB of
+// shared memory and writes it out itself, as 16-byte vectors, before it takes the next unit.
+namespace r8 {
+constexpr int R = 8, ND = 17, D = 289, TW = 32, BW = TW + 2 * R;
+// C = 32: 16-row tile, 8 warps (120 KB halo + 8 x 9 KB staging); C = 64: the halo pixels are twice as wide, so an 8-row
+// tile and 6 warps (162 KB + 6 x 9 KB)
+template <int C_>
+struct Cfg {
+  static constexpr int C = C_, RS = C + 8;
+  static constexpr int TH = C == 32 ? 16 : 8, BH = TH + 2 * R;
+  static constexpr int NWARPS = C == 32 ? 8 : 6, NT = 32 * NWARPS;
+  static constexpr int B_BYTES = BH * BW * RS * 2;
+  static constexpr int UNIT_BYTES = 16 * D * 2;                     // one warp's staging slot (a multiple of 16)
+  static constexpr int COORD_BYTES = BH * BW * 16;                  // aliases the staging slots (dead before the MMAs)
+  static constexpr int SMEM_BYTES = B_BYTES + NWARPS * UNIT_BYTES;
+  static_assert(COORD_BYTES <= NWARPS * UNIT_BYTES && UNIT_BYTES % 16 == 0 && SMEM_BYTES <= 232448, "shared memory");
+  static_assert((RS * 2) % 16 == 0 && ((RS * 2) / 16) % 2 == 1, "ldmatrix row stride");
+};
+}  // namespace r8
+
+template <int CC, bool HAS_FLOW, typename T, typename TF>
+__global__ void __launch_bounds__(r8::Cfg<CC>::NT, 1)
+fwd_mma16_r8_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* __restrict__ flow, float flow_scale,
+                    T* __restrict__ out, int B, int H, int W, int64_t ops, int tiles_x, int tiles_y) {
+  using K = r8::Cfg<CC>;
+  constexpr int R = r8::R, ND = r8::ND, D = r8::D, TH = K::TH, TW = r8::TW, BH = K::BH, BW = r8::BW, C = K::C, RS = K::RS,
+                NWARPS = K::NWARPS, NTHREADS = K::NT, B_BYTES = K::B_BYTES, UNIT_BYTES = K::UNIT_BYTES;
+  static_assert(sizeof(T) == 2, "16-bit features only");
+  extern __shared__ __align__(128) unsigned char smem[];
+  T* sB = reinterpret_cast<T*>(smem);                                   // [BH * BW][RS] warped halo tile
+  int4* sCoord = reinterpret_cast<int4*>(smem + B_BYTES);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  T* so = reinterpret_cast<T*>(smem + B_BYTES + warp * UNIT_BYTES);     // this warp's [16 px][289] staging slot
+  const int t = blockIdx.x;
+  const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
+  const int x0 = tx * TW, y0 = ty * TH;
+
+  // ---- phase 1: sampling coordinates of every halo pixel (w = 0: outside the image -> zeros) ----
+  for (int i = tid; i < BH * BW; i += NTHREADS) {
+    const int rb = i / BW, u = i - rb * BW;
+    const int y = y0 - R + rb, x = x0 - R + u;
+    int4 cd = make_int4(0, 0, 0, 0);
+    if (y >= 0 && y < H && x >= 0 && x < W) {
+      if (HAS_FLOW) {
+        const SampleCoord s = sample_coord<T, TF>(flow, flow_scale, b, y, x, H, W);
+        cd = make_int4(s.pix, __float_as_int(s.ax), __float_as_int(s.ay), 1);
+      } else {
+        cd = make_int4((b * H + y) * W + x, 0, 0, 2);
+      }
+    }
+    sCoord[i] = cd;
+  }
+  __syncthreads();
+
+  // ---- phase 2: warped halo tile, 8 channels (16 bytes) per item, 4 items (16 corner loads) in flight per thread ----
+  {
+    constexpr int CH8 = C / 8, NB = BH * BW * CH8, FB = 4;
+    static_assert(NB % (FB * NTHREADS) == 0, "gather items");
+    const size_t rowstride = (size_t)W * C;
+#pragma unroll 1
+    for (int i0 = tid; i0 < NB; i0 += FB * NTHREADS) {
+      float4 tl[FB][2], tr[FB][2], bl[FB][2], br[FB][2];
+      int4 cd[FB];
+#pragma unroll
+      for (int j = 0; j < FB; ++j) {
+        const int i = i0 + j * NTHREADS;
+        const int p = i / CH8, k8 = i - p * CH8;
+        cd[j] = sCoord[p];
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        tl[j][0] = tl[j][1] = tr[j][0] = tr[j][1] = bl[j][0] = bl[j][1] = br[j][0] = br[j][1] = z;
+        if (cd[j].w != 0) {
+          const T* base = c2 + (size_t)cd[j].x * C + 8 * k8;
+          ld8<T>(base, tl[j][0], tl[j][1]);
+          if (cd[j].w == 1) {
+            ld8<T>(base + C, tr[j][0], tr[j][1]);
+            ld8<T>(base + rowstride, bl[j][0], bl[j][1]);
+            ld8<T>(base + rowstride + C, br[j][0], br[j][1]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < FB; ++j) {
+        const int i = i0 + j * NTHREADS;
+        const int p = i / CH8, k8 = i - p * CH8;
+        float4 lo = tl[j][0], hi = tl[j][1];
+        if (cd[j].w == 1) {
+          const float ax = __int_as_float(cd[j].y), ay = __int_as_float(cd[j].z);
+          lo = bilerp4(tl[j][0], tr[j][0], bl[j][0], br[j][0], ax, ay);
+          hi = bilerp4(tl[j][1], tr[j][1], bl[j][1], br[j][1], ax, ay);
+        }
+        *reinterpret_cast<uint4*>(sB + (size_t)p * RS + 8 * k8) = pack8<T>(lo, hi);  // one rounding, like the reference's warp
+      }
+    }
+  }
+  __syncthreads();   // the coordinates are dead from here on: their memory becomes the staging slots
+
+  // ---- phase 3: band GEMMs, one (row, 16-pixel block) unit at a time per warp, written out by the same warp ----
+  const int g = lane >> 2, tq = lane & 3;
+  const float inv_c = 1.0f / (float)C;
+#pragma unroll 1
+  for (int un = warp; un < TH * (TW / 16); un += NWARPS) {
+    const int row = un >> 1, blk = un & 1;
+    const int y = y0 + row, xu = x0 + 16 * blk;
+    if (y >= H || xu >= W) continue;   // warp-uniform
+    uint32_t afr[C / 16][4];
+    {
+      const int xa = min(xu + g, W - 1), xb = min(xu + g + 8, W - 1);
+      const uint32_t* pa = reinterpret_cast<const uint32_t*>(c1 + (((size_t)b * H + y) * W + xa) * C);
+      const uint32_t* pb = reinterpret_cast<const uint32_t*>(c1 + (((size_t)b * H + y) * W + xb) * C);
+#pragma unroll
+      for (int ks = 0; ks < C / 16; ++ks) {
+        afr[ks][0] = __ldg(pa + ks * 8 + tq);
+        afr[ks][1] = __ldg(pb + ks * 8 + tq);
+        afr[ks][2] = __ldg(pa + ks * 8 + 4 + tq);
+        afr[ks][3] = __ldg(pb + ks * 8 + 4 + tq);
+      }
+    }
+#pragma unroll 1
+    for (int dyi = 0; dyi < ND; ++dyi) {
+      // warped row (row + dyi) of the halo tile, halo columns 16 blk .. 16 blk + 31  <->  x' = x0 + 16 blk - 8 + n
+      const T* brow = sB + (size_t)((row + dyi) * BW + 16 * blk) * RS;
+      float acc[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < C / 16; ++ks) {
+          uint32_t b0, b1;
+          const T* src = brow + (size_t)(8 * nt + (lane & 7)) * RS + 16 * ks + ((lane >> 3) & 1) * 8;
+          ldmatrix_x2(b0, b1, smem_u32(src));
+          mma16816<T>(acc[nt], afr[ks], b0, b1);
+        }
+      }
+      // accumulator (pixel m, neighbour n): m = g + 8 h, n = 8 nt + 2 t + j  ->  dx index = n - m in [0, 17)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int h = e >> 1, j = e & 1;
+          const int m = g + 8 * h, dxi = 8 * nt + 2 * tq + j - m;
+          if (dxi >= 0 && dxi < ND) {
+            const float v = acc[nt][e] * inv_c;
+            so[m * D + dyi * ND + dxi] = ElemTraits<T>::from_f(fmaxf(0.1f * v, v));
+          }
+        }
+    }
+    __syncwarp();
+    const int npx = min(16, W - xu);
+    T* dst = out + (((size_t)b * H + y) * W + xu) * ops;
+    if (ops == D && npx == 16 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      for (int i = lane; i < UNIT_BYTES / 16; i += 32) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(so)[i];
+    } else {
+      for (int i = lane; i < npx * D; i += 32) {
+        const int px = i / D, ch = i - px * D;
+        dst[(size_t)px * ops + ch] = so[i];
+      }
+    }
+    __syncwarp();   // the slot is rewritten by the next unit
+  }
+}
+
 // Returns 0 when launched, 1 when the shape is not covered, -1 on a CUDA error.
 template <typename T, typename TF>
 int launch(const T* c1, const T* c2, const TF* flow, float flow_scale, T* out, int B, int H, int W, int C, int64_t ops,
@@ -245,6 +410,28 @@ int launch(const T* c1, const T* c2, const TF* flow, float flow_scale, T* out, i
   if (C == 32)
     return flow ? go(fwd_mma16_kernel<32, true, T, TF>, Cfg<32>::SMEM_BYTES) : go(fwd_mma16_kernel<32, false, T, TF>, Cfg<32>::SMEM_BYTES);
   return flow ? go(fwd_mma16_kernel<64, true, T, TF>, Cfg<64>::SMEM_BYTES) : go(fwd_mma16_kernel<64, false, T, TF>, Cfg<64>::SMEM_BYTES);
+}
+
+// search_range 8: C in {32, 64}
+template <typename T, typename TF>
+int launch_r8(const T* c1, const T* c2, const TF* flow, float flow_scale, T* out, int B, int H, int W, int C, int64_t ops,
+              cudaStream_t st) {
+  if (sizeof(T) != 2 || (C != 32 && C != 64) || ops < r8::D) return 1;
+  if ((reinterpret_cast<uintptr_t>(c1) | reinterpret_cast<uintptr_t>(c2)) & 15) return 1;
+  const int th = C == 32 ? r8::Cfg<32>::TH : r8::Cfg<64>::TH;
+  const int tiles_x = (W + r8::TW - 1) / r8::TW, tiles_y = (H + th - 1) / th;
+  const long long tiles = (long long)tiles_x * tiles_y * B;
+  if (tiles <= 0 || tiles >= (1LL << 31)) return 1;
+  auto go = [&](auto kern, int nthreads, int smem_bytes) -> int {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return -1;
+    kern<<<(unsigned)tiles, nthreads, smem_bytes, st>>>(c1, c2, flow, flow_scale, out, B, H, W, ops, tiles_x, tiles_y);
+    return 0;
+  };
+  if (C == 32)
+    return flow ? go(fwd_mma16_r8_kernel<32, true, T, TF>, r8::Cfg<32>::NT, r8::Cfg<32>::SMEM_BYTES)
+                : go(fwd_mma16_r8_kernel<32, false, T, TF>, r8::Cfg<32>::NT, r8::Cfg<32>::SMEM_BYTES);
+  return flow ? go(fwd_mma16_r8_kernel<64, true, T, TF>, r8::Cfg<64>::NT, r8::Cfg<64>::SMEM_BYTES)
+              : go(fwd_mma16_r8_kernel<64, false, T, TF>, r8::Cfg<64>::NT, r8::Cfg<64>::SMEM_BYTES);
 }
 
 }  // namespace mma16

@@ -145,6 +145,10 @@ int fwd_typed(const void* c1, const void* c2, const void* flow, float flow_scale
   // fall back to the choice above
   const int impl_fallback = impl;
   if (g_fwd_impl.load() == 0 && sizeof(T) == 2 && tuned_ok && r == 4 && (C == 32 || C == 64) && H >= kTallMinH) impl = 4;
+  // search_range 8 (289 channels, configs[4]): 17 of 32 diagonals of the band GEMM are used, the CUDA-core tile kernel
+  // is FMA-bound at 11 % of its peak
+  // (small levels stay on the tile kernel: 2x34x60x32 takes 37 us there, 52 us here)
+  if (g_fwd_impl.load() == 0 && sizeof(T) == 2 && tuned_ok && r == 8 && (C == 32 || C == 64) && (int64_t)B * H * W >= 65536) impl = 4;
   if (impl == 3 && r != 4) impl = 2;  // the streaming kernel is written for search_range 4
   // un-warped small level (the pyramid top): too few tiles for the tiled kernel, one thread per output element wins
   if (g_fwd_impl.load() == 0 && flow == nullptr && vec_ok && (int64_t)B * H * W <= 16384) {
@@ -162,10 +166,13 @@ int fwd_typed(const void* c1, const void* c2, const void* flow, float flow_scale
     return PWC_OK;
   }
   if (impl >= 2 && !tuned_ok) impl = 1;
-  if (impl == 4) {  // 16-bit band GEMM on the tensor cores (fwd_mma16.cuh): r = 4, C in {32, 64}
+  if (impl == 4) {  // 16-bit band GEMM on the tensor cores (fwd_mma16.cuh): r = 4 or 8, C in {32, 64}
     int rc = 1;
     if constexpr (sizeof(T) == 2)
+    {
       if (r == 4) rc = pwc::mma16::launch<T, TF>((const T*)c1, (const T*)c2, (const TF*)flow, flow_scale, (T*)out, B, H, W, C, ops, st);
+      if (r == 8) rc = pwc::mma16::launch_r8<T, TF>((const T*)c1, (const T*)c2, (const TF*)flow, flow_scale, (T*)out, B, H, W, C, ops, st);
+    }
     if (rc == 0) { PWC_LAUNCH_CHECK(); return PWC_OK; }
     if (rc < 0) return fail(PWC_ERR_CUDA, "mma16 kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     impl = g_fwd_impl.load() == 0 ? impl_fallback : (r == 4 && H >= kTallMinH ? 3 : 2);  // shape not covered
