@@ -49,7 +49,7 @@ PRESETS = {
     3: dict(height=384, width=448, batch=8, search_range=4, dtype="fp16", mode="train", levels=(6, 5, 4, 3, 2), top_flow=False),
     4: dict(height=1088, width=1920, batch=16, search_range=8, dtype="fp16", mode="fwd", levels=(6, 5, 4, 3, 2), top_flow=False),
 }
-OPTION_DEFAULTS = {"fwd_impl": 0, "bwd_impl": 0, "stream_ctas": 0, "stream_prefetch": 4, "stream_debug": 0, "bwd_debug": 0, "bwd_prefetch": 1,
+OPTION_DEFAULTS = {"fwd_impl": 0, "bwd_impl": 0, "stream_ctas": 0, "stream_prefetch": 4, "stream_debug": 0, "bwd_debug": 0, "bwd_prefetch": 1, "mma_tile": 1,
                    "overlap_levels": 1, "bwd_tiled": 1, "side_reverse": 1, "tile_small": 1, "side_sms": None}
 
 

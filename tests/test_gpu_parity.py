@@ -305,6 +305,54 @@ def test_fp16_levels(impl, dev):
         assert_close(out, ref, 1e-2, f"fp16 level {d['lvl']}")
 
 
+@pytest.mark.parametrize("mma_tile", [1, 0])
+@pytest.mark.parametrize("impl", [0, 4])
+def test_fp16_band_gemm(impl, mma_tile, dev):
+    """16-bit band GEMM on the tensor cores (fwd_mma16.cuh; the default for 16-bit tall levels with C in {32, 64, 96}):
+    both tile variants, ragged widths (partial 16-pixel blocks, scalar store path), no flow, strided output, bf16."""
+    _ffi.set_option("mma_tile", mma_tile)
+    try:
+        for (b, h, w, c, fk) in ((2, 40, 72, 32, "smooth"), (1, 30, 50, 64, "stress"), (1, 28, 36, 96, "smooth"),
+                                 (1, 33, 64, 32, None), (2, 29, 23, 64, "stress")):
+            d = synth.make_level(b, h, w, c, 500 + c + w, np.float16, fk)
+            ref = O.warp_cost_volume(d["c1"], d["c2"], d["flow"], 4, 2.5)
+            out = run_fwd(d, 4, 2.5, dev, impl)
+            assert out.dtype == np.float16
+            assert_close(out, ref, 1e-2, f"fp16 band GEMM impl {impl} tile {mma_tile} {b}x{h}x{w}x{c} {fk}")
+        # cost volume straight into its slice of the concat buffer
+        d = synth.make_level(2, 32, 48, 32, 77, np.float16, "smooth")
+        buf = torch.full((2, 32, 48, 81 + 32 + 2), -7.0, device=dev, dtype=torch.float16)
+        _ffi.set_option("fwd_impl", impl)
+        cost_volume(to_dev(d["c1"], dev), dense_image_warp(to_dev(d["c2"], dev), to_dev(d["flow"], dev)), 4, "corr", out=buf[..., :81])
+        assert_close(buf[..., :81].cpu().numpy(), O.warp_cost_volume(d["c1"], d["c2"], d["flow"], 4), 1e-2, "slice")
+        assert torch.all(buf[..., 81:] == -7.0)
+        # bf16 features, fp32 flow
+        d = synth.make_level(1, 32, 64, 64, 78, np.float32, "smooth")
+        t = {k: to_dev(d[k], dev).bfloat16() for k in ("c1", "c2")}
+        out = warp_cost_volume(t["c1"], t["c2"], to_dev(d["flow"], dev), 4, 1.25)
+        ref = O.warp_cost_volume(*(t[k].float().cpu().numpy() for k in ("c1", "c2")), d["flow"], 4, 1.25)
+        assert_close(out.float().cpu().numpy(), ref, 4e-2, "bf16 band GEMM")
+    finally:
+        _ffi.set_option("mma_tile", 1)
+        _ffi.set_option("fwd_impl", 0)
+
+
+def test_fp16_band_gemm_search_range_8(dev):
+    """search_range 8 (BASELINE configs[4]): auto takes the band GEMM from 64 K pixels on, fwd_impl 4 forces it"""
+    try:
+        for (b, h, w, c, fk) in ((1, 20, 40, 32, "smooth"), (1, 17, 30, 64, "stress"), (2, 19, 21, 32, None)):
+            d = synth.make_level(b, h, w, c, 600 + c + w, np.float16, fk, search_range=8)
+            ref = O.warp_cost_volume(d["c1"], d["c2"], d["flow"], 8, 2.5)
+            out = run_fwd(d, 8, 2.5, dev, 4)
+            assert out.shape[-1] == 289 and out.dtype == np.float16
+            assert_close(out, ref, 1e-2, f"fp16 band GEMM r=8 {b}x{h}x{w}x{c} {fk}")
+        d = synth.make_level(2, 136, 256, 32, 601, np.float16, "smooth", search_range=8)   # 69 632 pixels: auto
+        out = run_fwd(d, 8, 5.0, dev, 0)
+        assert_close(out[:1], O.warp_cost_volume(d["c1"][:1], d["c2"][:1], d["flow"][:1], 8, 5.0), 1e-2, "r=8 auto")
+    finally:
+        _ffi.set_option("fwd_impl", 0)
+
+
 def test_fp16_backward(dev):
     d = synth.make_level(2, 24, 32, 96, 77, np.float16, "smooth", with_grad=True)
     f32 = {k: d[k].astype(np.float32) for k in ("c1", "c2", "flow", "g")}
@@ -391,7 +439,7 @@ def test_non_finite_features_do_not_leak_into_the_zero_padding(dev):
 
 def test_options_round_trip_and_host_path_validation(dev):
     for key, val in (("fwd_impl", 2), ("bwd_impl", 1), ("overlap_levels", 0), ("side_sms", 8), ("side_reverse", 0),
-                     ("tile_small", 0), ("bwd_tiled", 0), ("stream_ctas", 100), ("stream_prefetch", 2), ("stream_debug", 0), ("bwd_debug", 0), ("bwd_prefetch", 1)):
+                     ("tile_small", 0), ("bwd_tiled", 0), ("stream_ctas", 100), ("stream_prefetch", 2), ("stream_debug", 0), ("bwd_debug", 0), ("bwd_prefetch", 1), ("mma_tile", 0)):
         old = _ffi.get_option(key)
         _ffi.set_option(key, val)
         assert _ffi.get_option(key) == val

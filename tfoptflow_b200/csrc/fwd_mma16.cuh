@@ -233,31 +233,34 @@ fwd_mma16_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* _
 // 16 x 32 tile resident (32 x 48 pixels, 120 KB) and there is no tile-wide staging buffer: each warp stages one
 // (row, 16-pixel block) unit - 16 pixels x 289 channels = 9 248 contiguous bytes of the output - in its own 9 KB of
 // shared memory and writes it out itself, as 16-byte vectors, before it takes the next unit.
-namespace r8 {
-constexpr int R = 8, ND = 17, D = 289, TW = 32, BW = TW + 2 * R;
-// C = 32: 16-row tile, 8 warps (120 KB halo + 8 x 9 KB staging); C = 64: the halo pixels are twice as wide, so an 8-row
-// tile and 6 warps (162 KB + 6 x 9 KB)
-template <int C_>
+namespace band {
+constexpr int TW = 32;
+// R = 8, C = 32: 16-row tile, 8 warps (120 KB halo + 8 x 9 KB staging); C = 64: the halo pixels are twice as wide, so an
+// 8-row tile and 6 warps (162 KB + 6 x 9 KB).  R = 4 (option mma_tile 1): 16 / 8 rows, two CTAs per SM.
+template <int R_, int C_>
 struct Cfg {
+  static constexpr int R = R_, ND = 2 * R + 1, D = ND * ND, BW = TW + 2 * R, NTILES = (16 + 2 * R) / 8;
   static constexpr int C = C_, RS = C + 8;
   static constexpr int TH = C == 32 ? 16 : 8, BH = TH + 2 * R;
-  static constexpr int NWARPS = C == 32 ? 8 : 6, NT = 32 * NWARPS;
+  static constexpr int NWARPS = (R == 8 && C == 64) ? 6 : 8, NT = 32 * NWARPS;
+  static constexpr int CTAS = (R == 4 && C <= 64) ? 2 : 1;
   static constexpr int B_BYTES = BH * BW * RS * 2;
-  static constexpr int UNIT_BYTES = 16 * D * 2;                     // one warp's staging slot (a multiple of 16)
+  static constexpr int UNIT_BYTES = (16 * D * 2 + 15) / 16 * 16;    // one warp's staging slot: [16 px][D] 16-bit
   static constexpr int COORD_BYTES = BH * BW * 16;                  // aliases the staging slots (dead before the MMAs)
-  static constexpr int SMEM_BYTES = B_BYTES + NWARPS * UNIT_BYTES;
-  static_assert(COORD_BYTES <= NWARPS * UNIT_BYTES && UNIT_BYTES % 16 == 0 && SMEM_BYTES <= 232448, "shared memory");
+  static constexpr int STAGE_BYTES = NWARPS * UNIT_BYTES > COORD_BYTES ? NWARPS * UNIT_BYTES : COORD_BYTES;
+  static constexpr int SMEM_BYTES = B_BYTES + STAGE_BYTES;
+  static_assert((16 * D * 2) % 16 == 0 && SMEM_BYTES * CTAS <= 232448 - 1024 * CTAS, "shared memory");
   static_assert((RS * 2) % 16 == 0 && ((RS * 2) / 16) % 2 == 1, "ldmatrix row stride");
 };
-}  // namespace r8
+}  // namespace band
 
-template <int CC, bool HAS_FLOW, typename T, typename TF>
-__global__ void __launch_bounds__(r8::Cfg<CC>::NT, 1)
-fwd_mma16_r8_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* __restrict__ flow, float flow_scale,
+template <int RR, int CC, bool HAS_FLOW, typename T, typename TF>
+__global__ void __launch_bounds__(band::Cfg<RR, CC>::NT, band::Cfg<RR, CC>::CTAS)
+fwd_mma16_band_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* __restrict__ flow, float flow_scale,
                     T* __restrict__ out, int B, int H, int W, int64_t ops, int tiles_x, int tiles_y) {
-  using K = r8::Cfg<CC>;
-  constexpr int R = r8::R, ND = r8::ND, D = r8::D, TH = K::TH, TW = r8::TW, BH = K::BH, BW = r8::BW, C = K::C, RS = K::RS,
-                NWARPS = K::NWARPS, NTHREADS = K::NT, B_BYTES = K::B_BYTES, UNIT_BYTES = K::UNIT_BYTES;
+  using K = band::Cfg<RR, CC>;
+  constexpr int R = K::R, ND = K::ND, D = K::D, TH = K::TH, TW = band::TW, BH = K::BH, BW = K::BW, C = K::C, RS = K::RS,
+                NWARPS = K::NWARPS, NTHREADS = K::NT, B_BYTES = K::B_BYTES, UNIT_BYTES = K::UNIT_BYTES, NTILES = K::NTILES;
   static_assert(sizeof(T) == 2, "16-bit features only");
   extern __shared__ __align__(128) unsigned char smem[];
   T* sB = reinterpret_cast<T*>(smem);                                   // [BH * BW][RS] warped halo tile
@@ -285,10 +288,9 @@ fwd_mma16_r8_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF
   }
   __syncthreads();
 
-  // ---- phase 2: warped halo tile, 8 channels (16 bytes) per item, 4 items (16 corner loads) in flight per thread ----
+  // ---- phase 2: warped halo tile, 8 channels (16 bytes) per item, FB items (4 corner loads each) in flight per thread ----
   {
-    constexpr int CH8 = C / 8, NB = BH * BW * CH8, FB = 4;
-    static_assert(NB % (FB * NTHREADS) == 0, "gather items");
+    constexpr int CH8 = C / 8, NB = BH * BW * CH8, FB = K::CTAS == 2 ? 2 : 4;   // 128 registers with two CTAs per SM
     const size_t rowstride = (size_t)W * C;
 #pragma unroll 1
     for (int i0 = tid; i0 < NB; i0 += FB * NTHREADS) {
@@ -298,7 +300,7 @@ fwd_mma16_r8_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF
       for (int j = 0; j < FB; ++j) {
         const int i = i0 + j * NTHREADS;
         const int p = i / CH8, k8 = i - p * CH8;
-        cd[j] = sCoord[p];
+        cd[j] = i < NB ? sCoord[p] : make_int4(0, 0, 0, 0);
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
         tl[j][0] = tl[j][1] = tr[j][0] = tr[j][1] = bl[j][0] = bl[j][1] = br[j][0] = br[j][1] = z;
         if (cd[j].w != 0) {
@@ -314,6 +316,7 @@ fwd_mma16_r8_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF
 #pragma unroll
       for (int j = 0; j < FB; ++j) {
         const int i = i0 + j * NTHREADS;
+        if (i >= NB) continue;
         const int p = i / CH8, k8 = i - p * CH8;
         float4 lo = tl[j][0], hi = tl[j][1];
         if (cd[j].w == 1) {
@@ -350,11 +353,11 @@ fwd_mma16_r8_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF
     }
 #pragma unroll 1
     for (int dyi = 0; dyi < ND; ++dyi) {
-      // warped row (row + dyi) of the halo tile, halo columns 16 blk .. 16 blk + 31  <->  x' = x0 + 16 blk - 8 + n
+      // warped row (row + dyi) of the halo tile, halo columns 16 blk .. 16 blk + 15 + 2 R  <->  x' = x0 + 16 blk - R + n
       const T* brow = sB + (size_t)((row + dyi) * BW + 16 * blk) * RS;
-      float acc[4][4];
+      float acc[NTILES][4];
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
+      for (int nt = 0; nt < NTILES; ++nt) {
         acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
 #pragma unroll
         for (int ks = 0; ks < C / 16; ++ks) {
@@ -364,9 +367,9 @@ fwd_mma16_r8_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF
           mma16816<T>(acc[nt], afr[ks], b0, b1);
         }
       }
-      // accumulator (pixel m, neighbour n): m = g + 8 h, n = 8 nt + 2 t + j  ->  dx index = n - m in [0, 17)
+      // accumulator (pixel m, neighbour n): m = g + 8 h, n = 8 nt + 2 t + j  ->  dx index = n - m in [0, ND)
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
+      for (int nt = 0; nt < NTILES; ++nt)
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int h = e >> 1, j = e & 1;
@@ -381,7 +384,7 @@ fwd_mma16_r8_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF
     const int npx = min(16, W - xu);
     T* dst = out + (((size_t)b * H + y) * W + xu) * ops;
     if (ops == D && npx == 16 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-      for (int i = lane; i < UNIT_BYTES / 16; i += 32) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(so)[i];
+      for (int i = lane; i < 16 * D * 2 / 16; i += 32) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(so)[i];
     } else {
       for (int i = lane; i < npx * D; i += 32) {
         const int px = i / D, ch = i - px * D;
@@ -412,26 +415,37 @@ int launch(const T* c1, const T* c2, const TF* flow, float flow_scale, T* out, i
   return flow ? go(fwd_mma16_kernel<64, true, T, TF>, Cfg<64>::SMEM_BYTES) : go(fwd_mma16_kernel<64, false, T, TF>, Cfg<64>::SMEM_BYTES);
 }
 
-// search_range 8: C in {32, 64}
-template <typename T, typename TF>
-int launch_r8(const T* c1, const T* c2, const TF* flow, float flow_scale, T* out, int B, int H, int W, int C, int64_t ops,
-              cudaStream_t st) {
-  if (sizeof(T) != 2 || (C != 32 && C != 64) || ops < r8::D) return 1;
+// the resident-halo variant: search_range 8 (C in {32, 64}), and search_range 4 as an alternative to the kernel above
+template <int RR, typename T, typename TF>
+int launch_band(const T* c1, const T* c2, const TF* flow, float flow_scale, T* out, int B, int H, int W, int C, int64_t ops,
+                cudaStream_t st) {
+  if (sizeof(T) != 2 || (C != 32 && C != 64 && !(C == 96 && RR == 4)) || ops < band::Cfg<RR, 32>::D) return 1;
   if ((reinterpret_cast<uintptr_t>(c1) | reinterpret_cast<uintptr_t>(c2)) & 15) return 1;
-  const int th = C == 32 ? r8::Cfg<32>::TH : r8::Cfg<64>::TH;
-  const int tiles_x = (W + r8::TW - 1) / r8::TW, tiles_y = (H + th - 1) / th;
+  const int th = C == 32 ? band::Cfg<RR, 32>::TH : band::Cfg<RR, 64>::TH;   // 8 rows for every C > 32
+  const int tiles_x = (W + band::TW - 1) / band::TW, tiles_y = (H + th - 1) / th;
   const long long tiles = (long long)tiles_x * tiles_y * B;
   if (tiles <= 0 || tiles >= (1LL << 31)) return 1;
   auto go = [&](auto kern, int nthreads, int smem_bytes) -> int {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess) return -1;
     kern<<<(unsigned)tiles, nthreads, smem_bytes, st>>>(c1, c2, flow, flow_scale, out, B, H, W, ops, tiles_x, tiles_y);
     return 0;
   };
   if (C == 32)
-    return flow ? go(fwd_mma16_r8_kernel<32, true, T, TF>, r8::Cfg<32>::NT, r8::Cfg<32>::SMEM_BYTES)
-                : go(fwd_mma16_r8_kernel<32, false, T, TF>, r8::Cfg<32>::NT, r8::Cfg<32>::SMEM_BYTES);
-  return flow ? go(fwd_mma16_r8_kernel<64, true, T, TF>, r8::Cfg<64>::NT, r8::Cfg<64>::SMEM_BYTES)
-              : go(fwd_mma16_r8_kernel<64, false, T, TF>, r8::Cfg<64>::NT, r8::Cfg<64>::SMEM_BYTES);
+    return flow ? go(fwd_mma16_band_kernel<RR, 32, true, T, TF>, band::Cfg<RR, 32>::NT, band::Cfg<RR, 32>::SMEM_BYTES)
+                : go(fwd_mma16_band_kernel<RR, 32, false, T, TF>, band::Cfg<RR, 32>::NT, band::Cfg<RR, 32>::SMEM_BYTES);
+  if constexpr (RR == 4) {
+    if (C == 96)
+      return flow ? go(fwd_mma16_band_kernel<4, 96, true, T, TF>, band::Cfg<4, 96>::NT, band::Cfg<4, 96>::SMEM_BYTES)
+                  : go(fwd_mma16_band_kernel<4, 96, false, T, TF>, band::Cfg<4, 96>::NT, band::Cfg<4, 96>::SMEM_BYTES);
+  }
+  return flow ? go(fwd_mma16_band_kernel<RR, 64, true, T, TF>, band::Cfg<RR, 64>::NT, band::Cfg<RR, 64>::SMEM_BYTES)
+              : go(fwd_mma16_band_kernel<RR, 64, false, T, TF>, band::Cfg<RR, 64>::NT, band::Cfg<RR, 64>::SMEM_BYTES);
+}
+template <typename T, typename TF>
+int launch_r8(const T* c1, const T* c2, const TF* flow, float flow_scale, T* out, int B, int H, int W, int C, int64_t ops,
+              cudaStream_t st) {
+  return launch_band<8, T, TF>(c1, c2, flow, flow_scale, out, B, H, W, C, ops, st);
 }
 
 }  // namespace mma16

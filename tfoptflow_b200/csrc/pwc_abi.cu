@@ -41,6 +41,7 @@ std::atomic<int> g_fwd_impl{0};
 std::atomic<int> g_stream_ctas{0};
 std::atomic<int> g_stream_pf{4};
 std::atomic<int> g_stream_dbg{0};
+std::atomic<int> g_mma_tile{1};  // 16-bit band GEMM, r = 4: 0 = 8x32 tile with a tile-wide staging buffer, 1 = resident-halo variant
 std::atomic<int> g_bwd_pf{1};    // fused backward: L2 prefetch distance of the producers (turns of their row loop)
 std::atomic<int> g_bwd_dbg{0};   // fused backward: timing experiments only (see bwd_fused.cuh Args::dbg)
 // levels at least this tall take the streaming kernel (it pays ~5 warm-up slabs per strip segment): measured
@@ -144,7 +145,7 @@ int fwd_typed(const void* c1, const void* c2, const void* flow, float flow_scale
   // fp16: 216 vs 277 us, level 3: 147 vs 160 us; same error against the fp16-regime oracle); shapes it does not cover
   // fall back to the choice above
   const int impl_fallback = impl;
-  if (g_fwd_impl.load() == 0 && sizeof(T) == 2 && tuned_ok && r == 4 && (C == 32 || C == 64) && H >= kTallMinH) impl = 4;
+  if (g_fwd_impl.load() == 0 && sizeof(T) == 2 && tuned_ok && r == 4 && (C == 32 || C == 64 || (C == 96 && g_mma_tile.load())) && H >= kTallMinH) impl = 4;
   // search_range 8 (289 channels, configs[4]): 17 of 32 diagonals of the band GEMM are used, the CUDA-core tile kernel
   // is FMA-bound at 11 % of its peak
   // (small levels stay on the tile kernel: 2x34x60x32 takes 37 us there, 52 us here)
@@ -170,7 +171,9 @@ int fwd_typed(const void* c1, const void* c2, const void* flow, float flow_scale
     int rc = 1;
     if constexpr (sizeof(T) == 2)
     {
-      if (r == 4) rc = pwc::mma16::launch<T, TF>((const T*)c1, (const T*)c2, (const TF*)flow, flow_scale, (T*)out, B, H, W, C, ops, st);
+      if (r == 4)
+        rc = g_mma_tile.load() ? pwc::mma16::launch_band<4, T, TF>((const T*)c1, (const T*)c2, (const TF*)flow, flow_scale, (T*)out, B, H, W, C, ops, st)
+                               : pwc::mma16::launch<T, TF>((const T*)c1, (const T*)c2, (const TF*)flow, flow_scale, (T*)out, B, H, W, C, ops, st);
       if (r == 8) rc = pwc::mma16::launch_r8<T, TF>((const T*)c1, (const T*)c2, (const TF*)flow, flow_scale, (T*)out, B, H, W, C, ops, st);
     }
     if (rc == 0) { PWC_LAUNCH_CHECK(); return PWC_OK; }
@@ -579,6 +582,10 @@ int pwc_set_option(const char* key, int value) {
     g_stream_dbg.store(value);
     return PWC_OK;
   }
+  if (!strcmp(key, "mma_tile")) {
+    g_mma_tile.store(value != 0);
+    return PWC_OK;
+  }
   if (!strcmp(key, "bwd_prefetch")) {
     if (value < 0 || value > 8) return fail(PWC_ERR_BAD_ARG, "bwd_prefetch must be 0..8");
     g_bwd_pf.store(value);
@@ -611,6 +618,7 @@ int pwc_get_option(const char* key, int* value) {
   if (!strcmp(key, "stream_debug")) { *value = g_stream_dbg.load(); return PWC_OK; }
   if (!strcmp(key, "bwd_debug")) { *value = g_bwd_dbg.load(); return PWC_OK; }
   if (!strcmp(key, "bwd_prefetch")) { *value = g_bwd_pf.load(); return PWC_OK; }
+  if (!strcmp(key, "mma_tile")) { *value = g_mma_tile.load(); return PWC_OK; }
   if (!strcmp(key, "overlap_levels")) { *value = g_overlap.load(); return PWC_OK; }
   if (!strcmp(key, "bwd_impl")) { *value = g_bwd_impl.load(); return PWC_OK; }
   if (!strcmp(key, "side_sms")) { *value = g_side_sms.load(); return PWC_OK; }
