@@ -84,3 +84,21 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_every_option_key_is_documented_and_readable(lib):
+    """every key pwc_set_option accepts is documented in include/pwc_b200.h, listed in bench.py's OPTION_DEFAULTS (so a
+    non-default value is echoed in the bench line) and readable through pwc_get_option (both work without a GPU)"""
+    import re
+    src = open(os.path.join(ROOT, "tfoptflow_b200", "csrc", "pwc_abi.cu")).read()
+    body = src[src.index("int pwc_set_option("):src.index("int pwc_get_option(")]
+    keys = sorted(set(re.findall(r'strcmp\(key, "([a-z0-9_]+)"\)', body)))
+    assert len(keys) >= 12
+    header = open(os.path.join(ROOT, "include", "pwc_b200.h")).read()
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    for k in keys:
+        assert f'"{k}"' in header, f"option {k} is not documented in include/pwc_b200.h"
+        assert f'"{k}"' in bench, f"option {k} is missing from bench.py OPTION_DEFAULTS"
+        v = ctypes.c_int(-12345)
+        assert lib.pwc_get_option(k.encode(), ctypes.byref(v)) == 0, k
+        assert v.value != -12345

@@ -233,6 +233,12 @@ fwd_mma16_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* _
 // 16 x 32 tile resident (32 x 48 pixels, 120 KB) and there is no tile-wide staging buffer: each warp stages one
 // (row, 16-pixel block) unit - 16 pixels x 289 channels = 9 248 contiguous bytes of the output - in its own 9 KB of
 // shared memory and writes it out itself, as 16-byte vectors, before it takes the next unit.
+#ifndef PWC_BAND_FB
+#define PWC_BAND_FB 2    /* gather items (4 corner loads each) in flight per thread when two CTAs share an SM */
+#endif
+#ifndef PWC_BAND_DYU
+#define PWC_BAND_DYU 1   /* unroll of the displacement-row loop of the MMA phase */
+#endif
 namespace band {
 constexpr int TW = 32;
 // R = 8, C = 32: 16-row tile, 8 warps (120 KB halo + 8 x 9 KB staging); C = 64: the halo pixels are twice as wide, so an
@@ -290,7 +296,7 @@ fwd_mma16_band_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const 
 
   // ---- phase 2: warped halo tile, 8 channels (16 bytes) per item, FB items (4 corner loads each) in flight per thread ----
   {
-    constexpr int CH8 = C / 8, NB = BH * BW * CH8, FB = K::CTAS == 2 ? 2 : 4;   // 128 registers with two CTAs per SM
+    constexpr int CH8 = C / 8, NB = BH * BW * CH8, FB = K::CTAS == 2 ? PWC_BAND_FB : 4;   // 128 registers with two CTAs per SM
     const size_t rowstride = (size_t)W * C;
 #pragma unroll 1
     for (int i0 = tid; i0 < NB; i0 += FB * NTHREADS) {
@@ -351,7 +357,8 @@ fwd_mma16_band_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const 
         afr[ks][3] = __ldg(pb + ks * 8 + 4 + tq);
       }
     }
-#pragma unroll 1
+    constexpr int DYU = PWC_BAND_DYU;
+#pragma unroll DYU
     for (int dyi = 0; dyi < ND; ++dyi) {
       // warped row (row + dyi) of the halo tile, halo columns 16 blk .. 16 blk + 15 + 2 R  <->  x' = x0 + 16 blk - R + n
       const T* brow = sB + (size_t)((row + dyi) * BW + 16 * blk) * RS;
