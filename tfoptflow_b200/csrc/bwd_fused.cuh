@@ -392,9 +392,9 @@ __device__ __forceinline__ void produce_window(const Args& a, const Unit& un, co
 // block (box 32 x 9 planes, whole aligned 128-byte lines - no partial sectors), clipped at the image edge by the
 // tensor map.  The K2 consumer wants, for dwarp row y and strip x0, A[ey][ex][px] = g' of the source pixel
 // (y + ey - 4, x0 + px + ex - 4) for displacement (8 - ey, 8 - ex): that is the box (x0 + ex - 4, dxi = 8 - ex,
-// dyi = 0 .. 8, row y) of this tensor, so K2 fetches an A row with 9 tensor loads that start at an arbitrary x - the
-// TMA unit does the shift and zero-fills what lies outside the image.  Blocks whose source row is outside the image
-// are written as zeros (from sZ) by the builder of the row that shares their index.
+// dyi = 0 .. 8, row y) of this tensor, so K2 fetches an A row with tensor loads that start (a multiple of 4 pixels) to
+// the side - the TMA unit does the coarse shift and zero-fills what lies outside the image, see produce_a_k2.  Blocks
+// whose source row is outside the image are written as zeros (from sZ) by the builder of the row that shares their index.
 // The A slot is swizzled the way the tensor map's 128-byte mode expects (16-byte chunk ^= bits 7..9 of the address).
 template <int NAW, typename T>
 __device__ __forceinline__ void produce_a_k1(const Args& a, const Unit& un, const Walk& w, float* sA, uint64_t* full_a,
