@@ -398,8 +398,8 @@ __device__ __forceinline__ void produce_window(const Args& a, const Unit& un, co
 // The A slot is swizzled the way the tensor map's 128-byte mode expects (16-byte chunk ^= bits 7..9 of the address).
 template <int NAW, typename T>
 __device__ __forceinline__ void produce_a_k1(const Args& a, const Unit& un, const Walk& w, float* sA, uint64_t* full_a,
-                                             const float4* sZ, uint64_t* done, int ai, int lane, bool& pending,
-                                             const CUtensorMap* tm) {
+                                             const float4* sZ, uint64_t* done, uint64_t* stored, int ai, int lane,
+                                             int& pending_jg, const CUtensorMap* tm) {
   const T* __restrict__ g = reinterpret_cast<const T*>(a.g);
   const T* __restrict__ out = reinterpret_cast<const T*>(a.out);
   const int psub = lane >> 3, dq = lane & 7;
@@ -410,7 +410,9 @@ __device__ __forceinline__ void produce_a_k1(const Args& a, const Unit& un, cons
     prefetch_span(g + rp, npx * D * (int)sizeof(T), lane);
     prefetch_span(out + rp, npx * D * (int)sizeof(T), lane);
   };
-  // `pending` (caller's, lives across bands): bulk stores of my previous row not yet known to have read their source
+  // `pending_jg` (caller's, lives across bands): the row whose tensor stores are not yet known to have read their A slot.
+  // stored[slot] tells the builder of the slot's next occupant that they have (one barrier per slot is enough: the
+  // task-done wait that precedes it orders the phases)
   const int j0 = first_mine(2 * w.Pb, ai, NAW);
   for (int k = 0; k < a.pf; ++k) prefetch_row(j0 + k * NAW);
   for (int j = j0; j < 2 * un.P; j += NAW) {
@@ -418,7 +420,8 @@ __device__ __forceinline__ void produce_a_k1(const Args& a, const Unit& un, cons
     if (a.pf > 0) prefetch_row(j + a.pf * NAW);
     if (jg >= NG) {
       const int p = (jg - NG) >> 1;
-      mbar_wait(&done[p % NT], (p / NT) & 1);
+      mbar_wait(&done[p % NT], (p / NT) & 1);                       // the consumers are done with the slot
+      mbar_wait(&stored[(jg - NG) % NG], ((jg - NG) / NG) & 1);     // and so are the tensor stores of its last occupant
     }
     const int slot = jg % NG;
     float* A = sA + (size_t)slot * (AROW * 4);
@@ -458,10 +461,13 @@ __device__ __forceinline__ void produce_a_k1(const Args& a, const Unit& un, cons
     if (j < un.rows) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my stores, before TMA reads them
     __syncwarp();
     if (j < un.rows) {
+      // my previous row's stores have had a whole row's time to read their slot: confirm it and hand the slot on
+      if (pending_jg >= 0) {
+        if (lane < ND) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&stored[pending_jg % NG]);
+      }
       if (lane < ND) {
-        // the previous row's copies have had a whole row's time to read their source; its slot is not rewritten before
-        // the task that uses it has finished (done barrier), which is later still
-        if (pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         const int yq = y + lane - R;  // plane block dyi = lane lands in target row y + dyi - 4
         if (yq >= 0 && yq < a.H && !(a.dbg & 16)) tma_store_4d(tm, A + lane * ND * TW, un.x0, 0, lane, un.b * a.H + yq);
         // target row y itself: block dyi = lane would come from source row y + 4 - dyi
@@ -469,7 +475,9 @@ __device__ __forceinline__ void produce_a_k1(const Args& a, const Unit& un, cons
         if ((ys < 0 || ys >= a.H) && !(a.dbg & 16)) tma_store_4d(tm, sZ, un.x0, 0, lane, un.b * a.H + y);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
-      pending = true;
+      pending_jg = jg;
+    } else if (lane == 0) {
+      mbar_arrive(&stored[slot]);   // nothing is stored from a row past the end of the band
     }
     mbar_arrive(&full_a[jg % (2 * NG)]);
   }
@@ -788,7 +796,7 @@ bwd_fused_kernel(const Args a, const __grid_constant__ CUtensorMap tmap, const _
     for (int i = 0; i < 2 * NW; ++i) mbar_init(&full_w[i], 32);
     for (int i = 0; i < 2 * NG; ++i) mbar_init(&full_a[i], 32);
     for (int i = 0; i < NT; ++i) mbar_init(&done[i], 1);
-    for (int i = 0; i < NDS; ++i) { mbar_init(&full_d[i], 16); mbar_init(&empty_d[i], 1); }
+    for (int i = 0; i < NDS; ++i) { mbar_init(&full_d[i], MODE == 0 ? 1 : 16); mbar_init(&empty_d[i], 1); }   // K1: `stored`
     if (MODE == 1)
       for (int i = 0; i < 2 * NG; ++i) mbar_init(&landed[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the async (TMA) proxy
@@ -816,15 +824,21 @@ bwd_fused_kernel(const Args a, const __grid_constant__ CUtensorMap tmap, const _
   if constexpr (MODE == 0) {
     constexpr int NGW = NHELP - NAW_;
     static_assert(NGW >= 1, "K1 warp split");
-    bool pending = false;
+    static_assert(NG <= 2 * NDS, "K1's stored barriers live where K2 has its staging barriers");
+    uint64_t* stored = full_d;
+    int pending_jg = -1;
     while (w.next(a, un)) {
       if (hi < NAW_)
-        produce_a_k1<NAW_, T>(a, un, w, reinterpret_cast<float*>(sA), full_a, sZ, done, hi, lane, pending, &tmap);
+        produce_a_k1<NAW_, T>(a, un, w, reinterpret_cast<float*>(sA), full_a, sZ, done, stored, hi, lane, pending_jg, &tmap);
       else produce_window<HAS_FLOW, NGW, NW, T, TF>(a, un, w, sW, full_w, done, hi - NAW_, lane);
       w.advance(un);
     }
     // my last tensor stores must have read their shared-memory source before the CTA's memory goes away
-    if (hi < NAW_ && pending && lane < ND) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (hi < NAW_ && pending_jg >= 0) {
+      if (lane < ND) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&stored[pending_jg % NG]);
+    }
   } else {
     constexpr int NSW = HAS_FLOW ? 2 * NCW : 0;   // one scatter warp per staging slot
     constexpr int NWW = NHELP - NAW_ - NSW;
