@@ -260,27 +260,15 @@ struct Cfg {
 };
 }  // namespace band
 
-template <int RR, int CC, bool HAS_FLOW, typename T, typename TF>
-__global__ void __launch_bounds__(band::Cfg<RR, CC>::NT, band::Cfg<RR, CC>::CTAS)
-fwd_mma16_band_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* __restrict__ flow, float flow_scale,
-                    T* __restrict__ out, int B, int H, int W, int64_t ops, int tiles_x, int tiles_y) {
-  using K = band::Cfg<RR, CC>;
-  constexpr int R = K::R, ND = K::ND, D = K::D, TH = K::TH, TW = band::TW, BH = K::BH, BW = K::BW, C = K::C, RS = K::RS,
-                NWARPS = K::NWARPS, NTHREADS = K::NT, B_BYTES = K::B_BYTES, UNIT_BYTES = K::UNIT_BYTES, NTILES = K::NTILES;
-  static_assert(sizeof(T) == 2, "16-bit features only");
-  extern __shared__ __align__(128) unsigned char smem[];
-  T* sB = reinterpret_cast<T*>(smem);                                   // [BH * BW][RS] warped halo tile
-  int4* sCoord = reinterpret_cast<int4*>(smem + B_BYTES);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  T* so = reinterpret_cast<T*>(smem + B_BYTES + warp * UNIT_BYTES);     // this warp's [16 px][289] staging slot
-  const int t = blockIdx.x;
-  const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
-  const int x0 = tx * TW, y0 = ty * TH;
-
-  // ---- phase 1: sampling coordinates of every halo pixel (w = 0: outside the image -> zeros) ----
-  for (int i = tid; i < BH * BW; i += NTHREADS) {
-    const int rb = i / BW, u = i - rb * BW;
-    const int y = y0 - R + rb, x = x0 - R + u;
+// ---- the three phases of a tile ---------------------------------------------------------------------------------
+// phase 1: sampling coordinates of every halo pixel (w = 0: outside the image -> zeros); `tid` / `nthr` = the thread's
+// index inside the group of threads that works on the phase
+template <typename K, bool HAS_FLOW, typename T, typename TF>
+__device__ __forceinline__ void band_coords(const TF* __restrict__ flow, float flow_scale, int b, int y0, int x0, int H, int W,
+                                            int4* __restrict__ sCoord, int tid, int nthr) {
+  for (int i = tid; i < K::BH * K::BW; i += nthr) {
+    const int rb = i / K::BW, u = i - rb * K::BW;
+    const int y = y0 - K::R + rb, x = x0 - K::R + u;
     int4 cd = make_int4(0, 0, 0, 0);
     if (y >= 0 && y < H && x >= 0 && x < W) {
       if (HAS_FLOW) {
@@ -292,55 +280,62 @@ fwd_mma16_band_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const 
     }
     sCoord[i] = cd;
   }
-  __syncthreads();
+}
 
-  // ---- phase 2: warped halo tile, 8 channels (16 bytes) per item, FB items (4 corner loads each) in flight per thread ----
-  {
-    constexpr int CH8 = C / 8, NB = BH * BW * CH8, FB = K::CTAS == 2 ? PWC_BAND_FB : 4;   // 128 registers with two CTAs per SM
-    const size_t rowstride = (size_t)W * C;
+// phase 2: warped halo tile, 8 channels (16 bytes) per item, FB items (4 corner loads each) in flight per thread
+template <typename K, int FB, typename T>
+__device__ __forceinline__ void band_gather(const T* __restrict__ c2, int W, const int4* __restrict__ sCoord,
+                                            T* __restrict__ sB, int tid, int nthr) {
+  constexpr int C = K::C, CH8 = C / 8, NB = K::BH * K::BW * CH8;
+  const size_t rowstride = (size_t)W * C;
 #pragma unroll 1
-    for (int i0 = tid; i0 < NB; i0 += FB * NTHREADS) {
-      float4 tl[FB][2], tr[FB][2], bl[FB][2], br[FB][2];
-      int4 cd[FB];
+  for (int i0 = tid; i0 < NB; i0 += FB * nthr) {
+    float4 tl[FB][2], tr[FB][2], bl[FB][2], br[FB][2];
+    int4 cd[FB];
 #pragma unroll
-      for (int j = 0; j < FB; ++j) {
-        const int i = i0 + j * NTHREADS;
-        const int p = i / CH8, k8 = i - p * CH8;
-        cd[j] = i < NB ? sCoord[p] : make_int4(0, 0, 0, 0);
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        tl[j][0] = tl[j][1] = tr[j][0] = tr[j][1] = bl[j][0] = bl[j][1] = br[j][0] = br[j][1] = z;
-        if (cd[j].w != 0) {
-          const T* base = c2 + (size_t)cd[j].x * C + 8 * k8;
-          ld8<T>(base, tl[j][0], tl[j][1]);
-          if (cd[j].w == 1) {
-            ld8<T>(base + C, tr[j][0], tr[j][1]);
-            ld8<T>(base + rowstride, bl[j][0], bl[j][1]);
-            ld8<T>(base + rowstride + C, br[j][0], br[j][1]);
-          }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < FB; ++j) {
-        const int i = i0 + j * NTHREADS;
-        if (i >= NB) continue;
-        const int p = i / CH8, k8 = i - p * CH8;
-        float4 lo = tl[j][0], hi = tl[j][1];
+    for (int j = 0; j < FB; ++j) {
+      const int i = i0 + j * nthr;
+      const int p = i / CH8, k8 = i - p * CH8;
+      cd[j] = i < NB ? sCoord[p] : make_int4(0, 0, 0, 0);
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      tl[j][0] = tl[j][1] = tr[j][0] = tr[j][1] = bl[j][0] = bl[j][1] = br[j][0] = br[j][1] = z;
+      if (cd[j].w != 0) {
+        const T* base = c2 + (size_t)cd[j].x * C + 8 * k8;
+        ld8<T>(base, tl[j][0], tl[j][1]);
         if (cd[j].w == 1) {
-          const float ax = __int_as_float(cd[j].y), ay = __int_as_float(cd[j].z);
-          lo = bilerp4(tl[j][0], tr[j][0], bl[j][0], br[j][0], ax, ay);
-          hi = bilerp4(tl[j][1], tr[j][1], bl[j][1], br[j][1], ax, ay);
+          ld8<T>(base + C, tr[j][0], tr[j][1]);
+          ld8<T>(base + rowstride, bl[j][0], bl[j][1]);
+          ld8<T>(base + rowstride + C, br[j][0], br[j][1]);
         }
-        *reinterpret_cast<uint4*>(sB + (size_t)p * RS + 8 * k8) = pack8<T>(lo, hi);  // one rounding, like the reference's warp
       }
     }
+#pragma unroll
+    for (int j = 0; j < FB; ++j) {
+      const int i = i0 + j * nthr;
+      if (i >= NB) continue;
+      const int p = i / CH8, k8 = i - p * CH8;
+      float4 lo = tl[j][0], hi = tl[j][1];
+      if (cd[j].w == 1) {
+        const float ax = __int_as_float(cd[j].y), ay = __int_as_float(cd[j].z);
+        lo = bilerp4(tl[j][0], tr[j][0], bl[j][0], br[j][0], ax, ay);
+        hi = bilerp4(tl[j][1], tr[j][1], bl[j][1], br[j][1], ax, ay);
+      }
+      *reinterpret_cast<uint4*>(sB + (size_t)p * K::RS + 8 * k8) = pack8<T>(lo, hi);  // one rounding, like the reference's warp
+    }
   }
-  __syncthreads();   // the coordinates are dead from here on: their memory becomes the staging slots
+}
 
-  // ---- phase 3: band GEMMs, one (row, 16-pixel block) unit at a time per warp, written out by the same warp ----
+// phase 3: band GEMMs, one (row, 16-pixel block) unit at a time per warp, written out by the same warp from its own
+// staging slot `so`; `wg` / `nwg` = the warp's index inside the group of warps that shares the tile
+template <typename K, typename T>
+__device__ __forceinline__ void band_units(const T* __restrict__ c1, T* __restrict__ out, const T* __restrict__ sB,
+                                           T* __restrict__ so, int b, int y0, int x0, int H, int W, int64_t ops, int wg,
+                                           int nwg, int lane) {
+  constexpr int ND = K::ND, D = K::D, TH = K::TH, TW = band::TW, BW = K::BW, C = K::C, RS = K::RS, NTILES = K::NTILES;
   const int g = lane >> 2, tq = lane & 3;
   const float inv_c = 1.0f / (float)C;
 #pragma unroll 1
-  for (int un = warp; un < TH * (TW / 16); un += NWARPS) {
+  for (int un = wg; un < TH * (TW / 16); un += nwg) {
     const int row = un >> 1, blk = un & 1;
     const int y = y0 + row, xu = x0 + 16 * blk;
     if (y >= H || xu >= W) continue;   // warp-uniform
@@ -400,6 +395,27 @@ fwd_mma16_band_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const 
     }
     __syncwarp();   // the slot is rewritten by the next unit
   }
+}
+
+template <int RR, int CC, bool HAS_FLOW, typename T, typename TF>
+__global__ void __launch_bounds__(band::Cfg<RR, CC>::NT, band::Cfg<RR, CC>::CTAS)
+fwd_mma16_band_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* __restrict__ flow, float flow_scale,
+                      T* __restrict__ out, int B, int H, int W, int64_t ops, int tiles_x, int tiles_y) {
+  using K = band::Cfg<RR, CC>;
+  static_assert(sizeof(T) == 2, "16-bit features only");
+  extern __shared__ __align__(128) unsigned char smem[];
+  T* sB = reinterpret_cast<T*>(smem);                                   // [BH * BW][RS] warped halo tile
+  int4* sCoord = reinterpret_cast<int4*>(smem + K::B_BYTES);           // aliases the staging slots
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  T* so = reinterpret_cast<T*>(smem + K::B_BYTES + warp * K::UNIT_BYTES);   // this warp's [16 px][D] staging slot
+  const int t = blockIdx.x;
+  const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
+  const int x0 = tx * band::TW, y0 = ty * K::TH;
+  band_coords<K, HAS_FLOW, T, TF>(flow, flow_scale, b, y0, x0, H, W, sCoord, tid, K::NT);
+  __syncthreads();
+  band_gather<K, (K::CTAS == 2 ? PWC_BAND_FB : 4), T>(c2, W, sCoord, sB, tid, K::NT);   // 128 registers with two CTAs per SM
+  __syncthreads();   // the coordinates are dead from here on: their memory becomes the staging slots
+  band_units<K, T>(c1, out, sB, so, b, y0, x0, H, W, ops, warp, K::NWARPS, lane);
 }
 
 // Returns 0 when launched, 1 when the shape is not covered, -1 on a CUDA error.

@@ -145,7 +145,7 @@ int fwd_typed(const void* c1, const void* c2, const void* flow, float flow_scale
   // fp16: 216 vs 277 us, level 3: 147 vs 160 us; same error against the fp16-regime oracle); shapes it does not cover
   // fall back to the choice above
   const int impl_fallback = impl;
-  if (g_fwd_impl.load() == 0 && sizeof(T) == 2 && tuned_ok && r == 4 && (C == 32 || C == 64 || (C == 96 && g_mma_tile.load())) && H >= kTallMinH) impl = 4;
+  if (g_fwd_impl.load() == 0 && sizeof(T) == 2 && tuned_ok && r == 4 && (C == 32 || C == 64 || (C == 96 && g_mma_tile.load() >= 1)) && H >= kTallMinH) impl = 4;
   // search_range 8 (289 channels, configs[4]): 17 of 32 diagonals of the band GEMM are used, the CUDA-core tile kernel
   // is FMA-bound at 11 % of its peak
   // (small levels stay on the tile kernel: 2x34x60x32 takes 37 us there, 52 us here)
@@ -171,9 +171,12 @@ int fwd_typed(const void* c1, const void* c2, const void* flow, float flow_scale
     int rc = 1;
     if constexpr (sizeof(T) == 2)
     {
-      if (r == 4)
-        rc = g_mma_tile.load() ? pwc::mma16::launch_band<4, T, TF>((const T*)c1, (const T*)c2, (const TF*)flow, flow_scale, (T*)out, B, H, W, C, ops, st)
-                               : pwc::mma16::launch<T, TF>((const T*)c1, (const T*)c2, (const TF*)flow, flow_scale, (T*)out, B, H, W, C, ops, st);
+      if (r == 4) {
+        const int mt = g_mma_tile.load();
+        rc = 1;
+        if (rc == 1 && mt >= 1) rc = pwc::mma16::launch_band<4, T, TF>((const T*)c1, (const T*)c2, (const TF*)flow, flow_scale, (T*)out, B, H, W, C, ops, st);
+        if (rc == 1 && mt == 0) rc = pwc::mma16::launch<T, TF>((const T*)c1, (const T*)c2, (const TF*)flow, flow_scale, (T*)out, B, H, W, C, ops, st);
+      }
       if (r == 8) rc = pwc::mma16::launch_r8<T, TF>((const T*)c1, (const T*)c2, (const TF*)flow, flow_scale, (T*)out, B, H, W, C, ops, st);
     }
     if (rc == 0) { PWC_LAUNCH_CHECK(); return PWC_OK; }
@@ -583,7 +586,8 @@ int pwc_set_option(const char* key, int value) {
     return PWC_OK;
   }
   if (!strcmp(key, "mma_tile")) {
-    g_mma_tile.store(value != 0);
+    if (value < 0 || value > 1) return fail(PWC_ERR_BAD_ARG, "mma_tile must be 0 or 1");
+    g_mma_tile.store(value);
     return PWC_OK;
   }
   if (!strcmp(key, "bwd_prefetch")) {
