@@ -121,17 +121,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
-// TMA bulk copy shared -> global (SASS: UBLKCP), tracked by the bulk async-group of the issuing thread
-__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
 // TMA tensor copies (SASS: UTMALDG / UTMASTG), 4-d, coordinates innermost first
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
@@ -153,13 +142,8 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, const void* 
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_commit_wait_read() {
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-
 // L2 prefetch of a contiguous span / of one 128-byte line per pixel (the producers are latency-bound: one warp per
-// row with a few dozen loads in flight; pulling the rows of two turns ahead into L2 cuts each exposure from DRAM
+// row with a few dozen loads in flight; pulling the rows of the next turn (option bwd_prefetch) into L2 cuts each exposure from DRAM
 // latency to L2 latency)
 __device__ __forceinline__ void prefetch_span(const void* p, int nbytes, int lane) {
   const char* c = reinterpret_cast<const char*>(p);
