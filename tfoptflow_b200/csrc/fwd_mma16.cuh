@@ -234,10 +234,13 @@ fwd_mma16_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* _
 // (row, 16-pixel block) unit - 16 pixels x 289 channels = 9 248 contiguous bytes of the output - in its own 9 KB of
 // shared memory and writes it out itself, as 16-byte vectors, before it takes the next unit.
 #ifndef PWC_BAND_FB
-#define PWC_BAND_FB 2    /* gather items (4 corner loads each) in flight per thread when two CTAs share an SM */
+#define PWC_BAND_FB 4    /* gather items (4 corner loads each, kept packed) in flight per thread when two CTAs share an SM */
+#endif
+#ifndef PWC_BAND_FB1
+#define PWC_BAND_FB1 6   /* the same for the one-CTA-per-SM configurations (r = 8, C = 96) */
 #endif
 #ifndef PWC_BAND_DYU
-#define PWC_BAND_DYU 1   /* unroll of the displacement-row loop of the MMA phase */
+#define PWC_BAND_DYU 3   /* unroll of the displacement-row loop of the MMA phase */
 #endif
 namespace band {
 constexpr int TW = 32;
@@ -282,7 +285,15 @@ __device__ __forceinline__ void band_coords(const TF* __restrict__ flow, float f
   }
 }
 
-// phase 2: warped halo tile, 8 channels (16 bytes) per item, FB items (4 corner loads each) in flight per thread
+// phase 2: warped halo tile, 8 channels (16 bytes) per item, FB items (4 corner loads each) in flight per thread.  The
+// corners stay packed (4 registers each) until they are blended, so 4 items = 16 loads fit the registers of a
+// two-CTAs-per-SM kernel
+template <typename T>
+__device__ __forceinline__ void unpack8(const uint4& u, float4& lo, float4& hi) {
+  const T* h = reinterpret_cast<const T*>(&u);
+  lo = make_float4(ElemTraits<T>::to_f(h[0]), ElemTraits<T>::to_f(h[1]), ElemTraits<T>::to_f(h[2]), ElemTraits<T>::to_f(h[3]));
+  hi = make_float4(ElemTraits<T>::to_f(h[4]), ElemTraits<T>::to_f(h[5]), ElemTraits<T>::to_f(h[6]), ElemTraits<T>::to_f(h[7]));
+}
 template <typename K, int FB, typename T>
 __device__ __forceinline__ void band_gather(const T* __restrict__ c2, int W, const int4* __restrict__ sCoord,
                                             T* __restrict__ sB, int tid, int nthr) {
@@ -290,22 +301,21 @@ __device__ __forceinline__ void band_gather(const T* __restrict__ c2, int W, con
   const size_t rowstride = (size_t)W * C;
 #pragma unroll 1
   for (int i0 = tid; i0 < NB; i0 += FB * nthr) {
-    float4 tl[FB][2], tr[FB][2], bl[FB][2], br[FB][2];
+    uint4 tl[FB], tr[FB], bl[FB], br[FB];
     int4 cd[FB];
 #pragma unroll
     for (int j = 0; j < FB; ++j) {
       const int i = i0 + j * nthr;
       const int p = i / CH8, k8 = i - p * CH8;
       cd[j] = i < NB ? sCoord[p] : make_int4(0, 0, 0, 0);
-      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      tl[j][0] = tl[j][1] = tr[j][0] = tr[j][1] = bl[j][0] = bl[j][1] = br[j][0] = br[j][1] = z;
+      tl[j] = tr[j] = bl[j] = br[j] = make_uint4(0u, 0u, 0u, 0u);   // +0.0 in either 16-bit format
       if (cd[j].w != 0) {
         const T* base = c2 + (size_t)cd[j].x * C + 8 * k8;
-        ld8<T>(base, tl[j][0], tl[j][1]);
+        tl[j] = __ldg(reinterpret_cast<const uint4*>(base));
         if (cd[j].w == 1) {
-          ld8<T>(base + C, tr[j][0], tr[j][1]);
-          ld8<T>(base + rowstride, bl[j][0], bl[j][1]);
-          ld8<T>(base + rowstride + C, br[j][0], br[j][1]);
+          tr[j] = __ldg(reinterpret_cast<const uint4*>(base + C));
+          bl[j] = __ldg(reinterpret_cast<const uint4*>(base + rowstride));
+          br[j] = __ldg(reinterpret_cast<const uint4*>(base + rowstride + C));
         }
       }
     }
@@ -314,13 +324,14 @@ __device__ __forceinline__ void band_gather(const T* __restrict__ c2, int W, con
       const int i = i0 + j * nthr;
       if (i >= NB) continue;
       const int p = i / CH8, k8 = i - p * CH8;
-      float4 lo = tl[j][0], hi = tl[j][1];
+      uint4 v = tl[j];   // no warp: the features as they are
       if (cd[j].w == 1) {
         const float ax = __int_as_float(cd[j].y), ay = __int_as_float(cd[j].z);
-        lo = bilerp4(tl[j][0], tr[j][0], bl[j][0], br[j][0], ax, ay);
-        hi = bilerp4(tl[j][1], tr[j][1], bl[j][1], br[j][1], ax, ay);
+        float4 a0, a1, b0, b1, c0, c1, d0, d1;
+        unpack8<T>(tl[j], a0, a1); unpack8<T>(tr[j], b0, b1); unpack8<T>(bl[j], c0, c1); unpack8<T>(br[j], d0, d1);
+        v = pack8<T>(bilerp4(a0, b0, c0, d0, ax, ay), bilerp4(a1, b1, c1, d1, ax, ay));   // one rounding, like the reference's warp
       }
-      *reinterpret_cast<uint4*>(sB + (size_t)p * K::RS + 8 * k8) = pack8<T>(lo, hi);  // one rounding, like the reference's warp
+      *reinterpret_cast<uint4*>(sB + (size_t)p * K::RS + 8 * k8) = v;
     }
   }
 }
@@ -413,7 +424,7 @@ fwd_mma16_band_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const 
   const int x0 = tx * band::TW, y0 = ty * K::TH;
   band_coords<K, HAS_FLOW, T, TF>(flow, flow_scale, b, y0, x0, H, W, sCoord, tid, K::NT);
   __syncthreads();
-  band_gather<K, (K::CTAS == 2 ? PWC_BAND_FB : 4), T>(c2, W, sCoord, sB, tid, K::NT);   // 128 registers with two CTAs per SM
+  band_gather<K, (K::CTAS == 2 ? PWC_BAND_FB : PWC_BAND_FB1), T>(c2, W, sCoord, sB, tid, K::NT);   // 128 registers with two CTAs per SM
   __syncthreads();   // the coordinates are dead from here on: their memory becomes the staging slots
   band_units<K, T>(c1, out, sB, so, b, y0, x0, H, W, ops, warp, K::NWARPS, lane);
 }
