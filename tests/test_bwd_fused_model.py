@@ -128,3 +128,39 @@ def test_model_matches_oracle(shape):
             dwarp[b, y0 + j, x0:x0 + n] = o[j][:n]
     assert np.abs(dc1 - dc1_ref).max() <= 2e-6 * np.abs(dc1_ref).max()
     assert np.abs(dwarp - dwarp_ref).max() <= 2e-6 * np.abs(dwarp_ref).max()
+
+
+def test_k2_tensor_load_decomposition_matches_the_shifted_row():
+    """produce_a_k2 / k2_issue_row / k2_finish_row: per ex one aligned box (32 px x 9 dyi) at x0 + 4 floor((ex - 4) / 4), two
+    remainder boxes (4 px x 3 planes x 9 dyi: x0 + 28 for ex = 1..3, x0 + 32 for ex = 5..7) and an in-place shift by
+    r = ex & 3 must give A[ex][dyi][px] = ws[y][dyi][8 - ex][x0 + px + ex - 4], zero outside [0, W)."""
+    rng = np.random.default_rng(3)
+    for W, x0 in ((64, 0), (64, 32), (40, 32), (33, 32), (20, 0)):
+        ws_row = rng.standard_normal((ND, ND, W))          # [dyi][dxi][x] of one target row
+
+        def box(xs, nx, dxi0, ndxi):                        # TMA tensor load: zero fill outside the tensor
+            out = np.zeros((ND, ndxi, nx))
+            for k in range(nx):
+                if 0 <= xs + k < W:
+                    out[:, :, k] = ws_row[:, dxi0:dxi0 + ndxi, xs + k]
+            return out
+
+        A = np.zeros((ND, ND, TW))                          # [ex][dyi][px]
+        for ex in range(ND):
+            c = 4 * ((ex - R) // 4)
+            assert c % 4 == 0 and c in (-4, 0, 4)
+            A[ex] = box(x0 + c, TW, 2 * R - ex, 1)[:, 0, :]
+        rem = [box(x0 + TW - R, 4, 5, 3), box(x0 + TW, 4, 1, 3)]   # planes dxi 5..7 / 1..3
+        for k, ex in enumerate((1, 2, 3, 5, 6, 7)):
+            r = ex & 3
+            rbox = rem[0 if k < 3 else 1]
+            new = np.empty((ND, TW))
+            for lane in range(TW):
+                for dyi in range(ND):
+                    new[dyi, lane] = A[ex][dyi, lane + r] if lane + r < TW else rbox[dyi, 3 - r, lane + r - TW]
+            A[ex] = new
+        for ex in range(ND):
+            for px in range(TW):
+                xs = x0 + px + ex - R
+                want = ws_row[:, 2 * R - ex, xs] if 0 <= xs < W else np.zeros(ND)
+                assert np.array_equal(A[ex][:, px], want), (W, x0, ex, px)
