@@ -59,10 +59,10 @@ uint64_t pwc_launch_count(void);
 /* Tuning / debug options (process-wide).  pwc_set_option returns PWC_ERR_BAD_ARG for an unknown key or an out-of-range
  * value; pwc_get_option reads back every key pwc_set_option accepts.
  *   "fwd_impl"        0 = auto (default: streaming kernel for r == 4 and H >= 28 - the band GEMM instead for 16-bit
- *                     features with C in {32, 64, 96} - tiled kernel for short levels and r == 8 (band GEMM for 16-bit features,
+ *                     features with C in {32, 64, 96, 128} at any height - tiled kernel for short levels and r == 8 (band GEMM for 16-bit features,
  *                     C in {32, 64}, >= 64 K pixels), generic otherwise),
  *                     1 = generic scalar kernel, 2 = tiled kernel, 3 = streaming kernel,
- *                     4 = tensor-core band GEMM for 16-bit features (r == 4: C in {32, 64, 96}, r == 8: C in {32, 64}; other
+ *                     4 = tensor-core band GEMM for 16-bit features (r == 4: C in {32, 64, 96, 128}, r == 8: C in {32, 64}; other
  *                     shapes fall back)
  *   "bwd_impl"        0 = auto (default: fused K1/K2 kernels for r == 4, C % 4 == 0 (16-bit: C % 8), dense g / out; else v1),
  *                     1 = unfused v1 kernels, 2 = fused kernels or PWC_ERR_BAD_ARG when the shape is not covered
@@ -78,7 +78,7 @@ uint64_t pwc_launch_count(void);
  *                     of the streaming kernel (RESULTS ARE WRONG; bench.py refuses to report with them set), bit 8
  *                     forces the LDG path for c1, bit 16 records the event trace read by pwc_debug_read_trace
  *   "mma_tile"        16-bit band GEMM for r == 4: 1 (default) = resident-halo kernel (16- or 8-row tiles, every warp stages and
- *                     writes its own units; also covers C == 96), 0 = 8x32 tiles with a tile-wide staging buffer
+ *                     writes its own units; also covers C == 96 and 128), 0 = 8x32 tiles with a tile-wide staging buffer
  *   "bwd_prefetch"    L2 prefetch distance of the fused backward's producer warps, in turns of their row loops
  *                     (default 1: two turns ahead re-reads 40 % of the
  *                     prefetched lines from DRAM, profiles/r02_notes.md; 0 = off, 0..8)

@@ -313,7 +313,7 @@ def test_fp16_band_gemm(impl, mma_tile, dev):
     _ffi.set_option("mma_tile", mma_tile)
     try:
         for (b, h, w, c, fk) in ((2, 40, 72, 32, "smooth"), (1, 30, 50, 64, "stress"), (1, 28, 36, 96, "smooth"),
-                                 (1, 33, 64, 32, None), (2, 29, 23, 64, "stress")):
+                                 (1, 33, 64, 32, None), (2, 29, 23, 64, "stress"), (2, 14, 32, 128, "smooth"), (1, 7, 20, 128, None)):
             d = synth.make_level(b, h, w, c, 500 + c + w, np.float16, fk)
             ref = O.warp_cost_volume(d["c1"], d["c2"], d["flow"], 4, 2.5)
             out = run_fwd(d, 4, 2.5, dev, impl)

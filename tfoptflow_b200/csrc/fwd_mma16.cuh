@@ -453,7 +453,7 @@ int launch(const T* c1, const T* c2, const TF* flow, float flow_scale, T* out, i
 template <int RR, typename T, typename TF>
 int launch_band(const T* c1, const T* c2, const TF* flow, float flow_scale, T* out, int B, int H, int W, int C, int64_t ops,
                 cudaStream_t st) {
-  if (sizeof(T) != 2 || (C != 32 && C != 64 && !(C == 96 && RR == 4)) || ops < band::Cfg<RR, 32>::D) return 1;
+  if (sizeof(T) != 2 || (C != 32 && C != 64 && !((C == 96 || C == 128) && RR == 4)) || ops < band::Cfg<RR, 32>::D) return 1;
   if ((reinterpret_cast<uintptr_t>(c1) | reinterpret_cast<uintptr_t>(c2)) & 15) return 1;
   const int th = C == 32 ? band::Cfg<RR, 32>::TH : band::Cfg<RR, 64>::TH;   // 8 rows for every C > 32
   const int tiles_x = (W + band::TW - 1) / band::TW, tiles_y = (H + th - 1) / th;
@@ -472,6 +472,9 @@ int launch_band(const T* c1, const T* c2, const TF* flow, float flow_scale, T* o
     if (C == 96)
       return flow ? go(fwd_mma16_band_kernel<4, 96, true, T, TF>, band::Cfg<4, 96>::NT, band::Cfg<4, 96>::SMEM_BYTES)
                   : go(fwd_mma16_band_kernel<4, 96, false, T, TF>, band::Cfg<4, 96>::NT, band::Cfg<4, 96>::SMEM_BYTES);
+    if (C == 128)
+      return flow ? go(fwd_mma16_band_kernel<4, 128, true, T, TF>, band::Cfg<4, 128>::NT, band::Cfg<4, 128>::SMEM_BYTES)
+                  : go(fwd_mma16_band_kernel<4, 128, false, T, TF>, band::Cfg<4, 128>::NT, band::Cfg<4, 128>::SMEM_BYTES);
   }
   return flow ? go(fwd_mma16_band_kernel<RR, 64, true, T, TF>, band::Cfg<RR, 64>::NT, band::Cfg<RR, 64>::SMEM_BYTES)
               : go(fwd_mma16_band_kernel<RR, 64, false, T, TF>, band::Cfg<RR, 64>::NT, band::Cfg<RR, 64>::SMEM_BYTES);

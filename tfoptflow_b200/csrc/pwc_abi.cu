@@ -141,11 +141,13 @@ int fwd_typed(const void* c1, const void* c2, const void* flow, float flow_scale
   // auto: the streaming kernel wins on tall levels (it pays ~5 warm-up slabs per strip segment), the tiled kernel
   // on short ones; measured crossover between H = 28 and H = 56 (profiles/r01_notes.md)
   if (impl == 0) impl = !tuned_ok ? 1 : (r == 4 && H >= kTallMinH ? 3 : 2);
-  // 16-bit features, C = 32 / 64: the tensor-core band GEMM beats the widening CUDA-core loop on tall levels (level 2
+  // 16-bit features, C = 32 / 64 / 96 / 128: the tensor-core band GEMM beats the widening CUDA-core loops (level 2
   // fp16: 216 vs 277 us, level 3: 147 vs 160 us; same error against the fp16-regime oracle); shapes it does not cover
   // fall back to the choice above
   const int impl_fallback = impl;
-  if (g_fwd_impl.load() == 0 && sizeof(T) == 2 && tuned_ok && r == 4 && (C == 32 || C == 64 || (C == 96 && g_mma_tile.load() >= 1)) && H >= kTallMinH) impl = 4;
+  if (g_fwd_impl.load() == 0 && sizeof(T) == 2 && tuned_ok && r == 4 &&
+      (g_mma_tile.load() >= 1 ? (C == 32 || C == 64 || C == 96 || C == 128) : ((C == 32 || C == 64) && H >= kTallMinH)))
+    impl = 4;   // any height: level 5 (14 rows, C = 128) takes 24 us against 56 us on the tiled kernel
   // search_range 8 (289 channels, configs[4]): 17 of 32 diagonals of the band GEMM are used, the CUDA-core tile kernel
   // is FMA-bound at 11 % of its peak
   // (small levels stay on the tile kernel: 2x34x60x32 takes 37 us there, 52 us here)
