@@ -60,9 +60,9 @@ uint64_t pwc_launch_count(void);
  * value; pwc_get_option reads back every key pwc_set_option accepts.
  *   "fwd_impl"        0 = auto (default: streaming kernel for r == 4 and H >= 28 - the band GEMM instead for 16-bit
  *                     features with C in {32, 64, 96, 128} at any height - tiled kernel for short levels and r == 8 (band GEMM for 16-bit features,
- *                     C in {32, 64}, >= 64 K pixels), generic otherwise),
+ *                     C in {32, 64, 96, 128}, >= 16 K pixels), generic otherwise),
  *                     1 = generic scalar kernel, 2 = tiled kernel, 3 = streaming kernel,
- *                     4 = tensor-core band GEMM for 16-bit features (r == 4: C in {32, 64, 96, 128}, r == 8: C in {32, 64}; other
+ *                     4 = tensor-core band GEMM for 16-bit features (r == 4 or 8, C in {32, 64, 96, 128}; other
  *                     shapes fall back)
  *   "bwd_impl"        0 = auto (default: fused K1/K2 kernels for r == 4, C % 4 == 0 (16-bit: C % 8), dense g / out; else v1),
  *                     1 = unfused v1 kernels, 2 = fused kernels or PWC_ERR_BAD_ARG when the shape is not covered

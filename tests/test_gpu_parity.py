@@ -340,7 +340,8 @@ def test_fp16_band_gemm(impl, mma_tile, dev):
 def test_fp16_band_gemm_search_range_8(dev):
     """search_range 8 (BASELINE configs[4]): auto takes the band GEMM from 64 K pixels on, fwd_impl 4 forces it"""
     try:
-        for (b, h, w, c, fk) in ((1, 20, 40, 32, "smooth"), (1, 17, 30, 64, "stress"), (2, 19, 21, 32, None)):
+        for (b, h, w, c, fk) in ((1, 20, 40, 32, "smooth"), (1, 17, 30, 64, "stress"), (2, 19, 21, 32, None),
+                                 (1, 20, 36, 96, "smooth"), (1, 9, 20, 128, "stress")):
             d = synth.make_level(b, h, w, c, 600 + c + w, np.float16, fk, search_range=8)
             ref = O.warp_cost_volume(d["c1"], d["c2"], d["flow"], 8, 2.5)
             out = run_fwd(d, 8, 2.5, dev, 4)

@@ -243,15 +243,17 @@ fwd_mma16_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const TF* _
 #define PWC_BAND_DYU 3   /* unroll of the displacement-row loop of the MMA phase */
 #endif
 namespace band {
-constexpr int TW = 32;
-// R = 8, C = 32: 16-row tile, 8 warps (120 KB halo + 8 x 9 KB staging); C = 64: the halo pixels are twice as wide, so an
-// 8-row tile and 6 warps (162 KB + 6 x 9 KB).  R = 4 (option mma_tile 1): 16 / 8 rows, two CTAs per SM.
+// R = 4: 16-row (C = 32) or 8-row tiles of 32 pixels, two CTAs per SM up to C = 64.  R = 8, C = 32: 16-row tile, 8 warps
+// (120 KB halo + 8 x 9 KB staging); C = 64: the halo pixels are twice as wide, so an 8-row tile and 6 warps (162 KB +
+// 6 x 9 KB); C = 96 / 128: 16-pixel-wide tiles of 6 / 4 rows, one unit per warp (the +-8 halo makes these expensive -
+// 5.5 / 10 halo pixels per output pixel - but still cheaper than 289 x C multiply-adds per pixel on the CUDA cores).
 template <int R_, int C_>
 struct Cfg {
-  static constexpr int R = R_, ND = 2 * R + 1, D = ND * ND, BW = TW + 2 * R, NTILES = (16 + 2 * R) / 8;
-  static constexpr int C = C_, RS = C + 8;
-  static constexpr int TH = C == 32 ? 16 : 8, BH = TH + 2 * R;
-  static constexpr int NWARPS = (R == 8 && C == 64) ? 6 : 8, NT = 32 * NWARPS;
+  static constexpr int R = R_, C = C_, RS = C + 8;
+  static constexpr int TW = (R == 8 && C >= 96) ? 16 : 32;
+  static constexpr int ND = 2 * R + 1, D = ND * ND, BW = TW + 2 * R, NTILES = (16 + 2 * R) / 8;
+  static constexpr int TH = C == 32 ? 16 : (R == 4 || C == 64) ? 8 : (C == 96 ? 6 : 4), BH = TH + 2 * R;
+  static constexpr int NWARPS = R == 4 ? 8 : (C == 32 ? 8 : (C == 128 ? 4 : 6)), NT = 32 * NWARPS;
   static constexpr int CTAS = (R == 4 && C <= 64) ? 2 : 1;
   static constexpr int B_BYTES = BH * BW * RS * 2;
   static constexpr int UNIT_BYTES = (16 * D * 2 + 15) / 16 * 16;    // one warp's staging slot: [16 px][D] 16-bit
@@ -342,12 +344,12 @@ template <typename K, typename T>
 __device__ __forceinline__ void band_units(const T* __restrict__ c1, T* __restrict__ out, const T* __restrict__ sB,
                                            T* __restrict__ so, int b, int y0, int x0, int H, int W, int64_t ops, int wg,
                                            int nwg, int lane) {
-  constexpr int ND = K::ND, D = K::D, TH = K::TH, TW = band::TW, BW = K::BW, C = K::C, RS = K::RS, NTILES = K::NTILES;
+  constexpr int ND = K::ND, D = K::D, TH = K::TH, TW = K::TW, BW = K::BW, C = K::C, RS = K::RS, NTILES = K::NTILES;
   const int g = lane >> 2, tq = lane & 3;
   const float inv_c = 1.0f / (float)C;
 #pragma unroll 1
   for (int un = wg; un < TH * (TW / 16); un += nwg) {
-    const int row = un >> 1, blk = un & 1;
+    const int row = un / (TW / 16), blk = un % (TW / 16);
     const int y = y0 + row, xu = x0 + 16 * blk;
     if (y >= H || xu >= W) continue;   // warp-uniform
     uint32_t afr[C / 16][4];
@@ -421,7 +423,7 @@ fwd_mma16_band_kernel(const T* __restrict__ c1, const T* __restrict__ c2, const 
   T* so = reinterpret_cast<T*>(smem + K::B_BYTES + warp * K::UNIT_BYTES);   // this warp's [16 px][D] staging slot
   const int t = blockIdx.x;
   const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
-  const int x0 = tx * band::TW, y0 = ty * K::TH;
+  const int x0 = tx * K::TW, y0 = ty * K::TH;
   band_coords<K, HAS_FLOW, T, TF>(flow, flow_scale, b, y0, x0, H, W, sCoord, tid, K::NT);
   __syncthreads();
   band_gather<K, (K::CTAS == 2 ? PWC_BAND_FB : PWC_BAND_FB1), T>(c2, W, sCoord, sB, tid, K::NT);   // 128 registers with two CTAs per SM
@@ -449,35 +451,34 @@ int launch(const T* c1, const T* c2, const TF* flow, float flow_scale, T* out, i
   return flow ? go(fwd_mma16_kernel<64, true, T, TF>, Cfg<64>::SMEM_BYTES) : go(fwd_mma16_kernel<64, false, T, TF>, Cfg<64>::SMEM_BYTES);
 }
 
-// the resident-halo variant: search_range 8 (C in {32, 64}), and search_range 4 as an alternative to the kernel above
+// the resident-halo variant: search_range 4 (C in {32, 64, 96, 128}) and search_range 8 (the same)
+template <int RR, int CC, typename T, typename TF>
+int launch_band_cfg(const T* c1, const T* c2, const TF* flow, float flow_scale, T* out, int B, int H, int W, int64_t ops,
+                    cudaStream_t st) {
+  using K = band::Cfg<RR, CC>;
+  const int tiles_x = (W + K::TW - 1) / K::TW, tiles_y = (H + K::TH - 1) / K::TH;
+  const long long tiles = (long long)tiles_x * tiles_y * B;
+  if (tiles <= 0 || tiles >= (1LL << 31)) return 1;
+  auto go = [&](auto kern) -> int {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess) return -1;
+    kern<<<(unsigned)tiles, K::NT, K::SMEM_BYTES, st>>>(c1, c2, flow, flow_scale, out, B, H, W, ops, tiles_x, tiles_y);
+    return 0;
+  };
+  return flow ? go(fwd_mma16_band_kernel<RR, CC, true, T, TF>) : go(fwd_mma16_band_kernel<RR, CC, false, T, TF>);
+}
 template <int RR, typename T, typename TF>
 int launch_band(const T* c1, const T* c2, const TF* flow, float flow_scale, T* out, int B, int H, int W, int C, int64_t ops,
                 cudaStream_t st) {
-  if (sizeof(T) != 2 || (C != 32 && C != 64 && !((C == 96 || C == 128) && RR == 4)) || ops < band::Cfg<RR, 32>::D) return 1;
+  if (sizeof(T) != 2 || ops < band::Cfg<RR, 32>::D) return 1;
   if ((reinterpret_cast<uintptr_t>(c1) | reinterpret_cast<uintptr_t>(c2)) & 15) return 1;
-  const int th = C == 32 ? band::Cfg<RR, 32>::TH : band::Cfg<RR, 64>::TH;   // 8 rows for every C > 32
-  const int tiles_x = (W + band::TW - 1) / band::TW, tiles_y = (H + th - 1) / th;
-  const long long tiles = (long long)tiles_x * tiles_y * B;
-  if (tiles <= 0 || tiles >= (1LL << 31)) return 1;
-  auto go = [&](auto kern, int nthreads, int smem_bytes) -> int {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return -1;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess) return -1;
-    kern<<<(unsigned)tiles, nthreads, smem_bytes, st>>>(c1, c2, flow, flow_scale, out, B, H, W, ops, tiles_x, tiles_y);
-    return 0;
-  };
-  if (C == 32)
-    return flow ? go(fwd_mma16_band_kernel<RR, 32, true, T, TF>, band::Cfg<RR, 32>::NT, band::Cfg<RR, 32>::SMEM_BYTES)
-                : go(fwd_mma16_band_kernel<RR, 32, false, T, TF>, band::Cfg<RR, 32>::NT, band::Cfg<RR, 32>::SMEM_BYTES);
-  if constexpr (RR == 4) {
-    if (C == 96)
-      return flow ? go(fwd_mma16_band_kernel<4, 96, true, T, TF>, band::Cfg<4, 96>::NT, band::Cfg<4, 96>::SMEM_BYTES)
-                  : go(fwd_mma16_band_kernel<4, 96, false, T, TF>, band::Cfg<4, 96>::NT, band::Cfg<4, 96>::SMEM_BYTES);
-    if (C == 128)
-      return flow ? go(fwd_mma16_band_kernel<4, 128, true, T, TF>, band::Cfg<4, 128>::NT, band::Cfg<4, 128>::SMEM_BYTES)
-                  : go(fwd_mma16_band_kernel<4, 128, false, T, TF>, band::Cfg<4, 128>::NT, band::Cfg<4, 128>::SMEM_BYTES);
+  switch (C) {
+    case 32: return launch_band_cfg<RR, 32, T, TF>(c1, c2, flow, flow_scale, out, B, H, W, ops, st);
+    case 64: return launch_band_cfg<RR, 64, T, TF>(c1, c2, flow, flow_scale, out, B, H, W, ops, st);
+    case 96: return launch_band_cfg<RR, 96, T, TF>(c1, c2, flow, flow_scale, out, B, H, W, ops, st);
+    case 128: return launch_band_cfg<RR, 128, T, TF>(c1, c2, flow, flow_scale, out, B, H, W, ops, st);
+    default: return 1;
   }
-  return flow ? go(fwd_mma16_band_kernel<RR, 64, true, T, TF>, band::Cfg<RR, 64>::NT, band::Cfg<RR, 64>::SMEM_BYTES)
-              : go(fwd_mma16_band_kernel<RR, 64, false, T, TF>, band::Cfg<RR, 64>::NT, band::Cfg<RR, 64>::SMEM_BYTES);
 }
 template <typename T, typename TF>
 int launch_r8(const T* c1, const T* c2, const TF* flow, float flow_scale, T* out, int B, int H, int W, int C, int64_t ops,

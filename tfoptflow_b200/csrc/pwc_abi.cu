@@ -151,7 +151,9 @@ int fwd_typed(const void* c1, const void* c2, const void* flow, float flow_scale
   // search_range 8 (289 channels, configs[4]): 17 of 32 diagonals of the band GEMM are used, the CUDA-core tile kernel
   // is FMA-bound at 11 % of its peak
   // (small levels stay on the tile kernel: 2x34x60x32 takes 37 us there, 52 us here)
-  if (g_fwd_impl.load() == 0 && sizeof(T) == 2 && tuned_ok && r == 8 && (C == 32 || C == 64) && (int64_t)B * H * W >= 65536) impl = 4;
+  if (g_fwd_impl.load() == 0 && sizeof(T) == 2 && tuned_ok && r == 8 && (C == 32 || C == 64 || C == 96 || C == 128) &&
+      (int64_t)B * H * W >= 16384)
+    impl = 4;
   if (impl == 3 && r != 4) impl = 2;  // the streaming kernel is written for search_range 4
   // un-warped small level (the pyramid top): too few tiles for the tiled kernel, one thread per output element wins
   if (g_fwd_impl.load() == 0 && flow == nullptr && vec_ok && (int64_t)B * H * W <= 16384) {
