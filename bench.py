@@ -16,6 +16,7 @@ Sintel 436x1024 padded to 448x1024, batch 32 per GPU, search_range 4, fp32, forw
                         with one NCCL all-reduce of the gradients (needs the PyTorch PWC-Net of model_pwcnet.py)  configs[3]
   --config 4            1088x1920, batch 16, r=8 (289 channels), fp16 forward              BASELINE configs[4]
   --mode allreduce      the training configuration's one exchange step (multi_gpus.average_gradients over NCCL)
+  --mode infer          the whole PWC-Net forward of model_pwcnet.py at the preset's shape (use with --config 0)
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` goes through the host-buffer path with
 H2D/D2H inside the timed region, `roofline` is the dominant kernel (pyramid level 2; its backward in fwdbwd mode)
@@ -60,7 +61,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=sorted(PRESETS))
-    ap.add_argument("--mode", default=None, choices=["fwd", "fwdbwd", "allreduce", "train"])
+    ap.add_argument("--mode", default=None, choices=["fwd", "fwdbwd", "allreduce", "train", "infer"])
     ap.add_argument("--dtype", default=None, choices=["fp32", "fp16"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --batch pairs on every GPU; strong: --batch pairs in total, batch/N per GPU (configs[2])")
@@ -227,6 +228,8 @@ def run_reference(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return 0
+    if a.mode == "infer":
+        return run_infer_reference(a)
     if a.mode in ("allreduce", "train"):
         print(json.dumps({"impl": "reference", "unavailable": "the reference's gradient averaging is a TF graph op on the "
                           "controller device (multi_gpus.py:68-86); there is no CPU-runnable collective to time"}), flush=True)
@@ -310,6 +313,8 @@ def run_ours(a):
         return run_allreduce(a, rank, world, local, dev)
     if a.mode == "train":
         return run_train(a, rank, world, local, dev)
+    if a.mode == "infer":
+        return run_infer(a, rank, world, local, dev)
     _ffi.load()
     if a.fwd_impl:
         _ffi.set_option("fwd_impl", a.fwd_impl)
@@ -597,6 +602,119 @@ def run_ours(a):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    return 0
+
+
+def _infer_line(a, world, value, ms, extra):
+    line = {"metric": "inference pairs/sec, pwcnet-%s-6-2 full model (image pairs per second)" % a.params, "value": value,
+            "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16" if a.dtype == "fp16" else "f32",
+            "data": "synthetic",
+            "config": {"workload": f"BASELINE.json configs[0]: pwcnet-{a.params}-6-2 forward, {a.height}x{a.width}, batch {a.batch}"
+                                   f"/GPU, random-init weights, search_range {a.search_range}, "
+                                   f"{'fp16 autocast' if a.dtype == 'fp16' else 'fp32'}", "pairs_per_step": world * a.batch}}
+    line.update(extra)
+    return line
+
+
+def run_infer(a, rank, world, local, dev):
+    """BASELINE configs[0]: the whole PWC-Net forward (tfoptflow_b200/model_pwcnet.py: cuDNN convolutions + this library's
+    fused warp + cost volume at every pyramid level) on synthetic image pairs with random-init weights."""
+    import torch
+    import torch.distributed as dist
+    from tfoptflow_b200 import _ffi, model_pwcnet as M
+    _ffi.load()
+    mixed = a.dtype == "fp16"
+    opts = M.pwcnet_options(a.params, use_mixed_precision=mixed, search_range=a.search_range)
+    torch.manual_seed(1969)
+    model = M.ModelPWCNet(opts).to(dev).to(memory_format=torch.channels_last).eval()
+    g = torch.Generator(device=dev).manual_seed(1969 + rank)
+    x = torch.rand((a.batch, 2, a.height, a.width, 3), device=dev, generator=g)
+    xh = x.cpu().pin_memory()
+    yh = torch.empty((a.batch, a.height, a.width, 2), dtype=torch.float32).pin_memory()
+
+    def step(from_host=False):
+        if from_host:
+            x.copy_(xh, non_blocking=True)
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16, enabled=mixed):
+            flow_pred, _ = model(x)
+        if from_host:
+            yh.copy_(flow_pred.float(), non_blocking=True)
+            torch.cuda.synchronize(dev)
+        return flow_pred
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    torch.cuda.synchronize(dev)
+    launches0 = _ffi.launch_count()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with sampler:
+        e0.record()
+        for _ in range(a.steps):
+            out = step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / a.steps
+    launches = _ffi.launch_count() - launches0
+    n_e2e = a.e2e_steps or min(a.steps, 20)
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        step(from_host=True)
+    t_e2e = (time.perf_counter() - t0) / n_e2e
+    if world > 1:
+        t = torch.tensor([ms, t_e2e * 1e3], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, t_e2e = float(t[0]), float(t[1]) / 1e3
+    if rank == 0:
+        print(json.dumps(_infer_line(a, world, world * a.batch / (ms / 1e3), ms, {
+            "flow_pred_finite": bool(torch.isfinite(out).all()), "clocks": sampler.summary(), "gpu_launches": int(launches),
+            "e2e": {"value": world * a.batch / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(xh.numel() * 4),
+                    "d2h_bytes_per_step": int(yh.numel() * 4), "steps": n_e2e, "ms_per_step": t_e2e * 1e3,
+                    "path": "pinned host image pairs -> H2D -> model forward -> flow D2H"}})), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_infer_reference(a):
+    """CPU arm of --mode infer: the same torch model on the host cores with the op-for-op port of the reference's
+    warp + cost-volume graph (oracle/ref_graph_torch.py) as the operator - TF 1.10 itself is not installable."""
+    import torch
+    from oracle import ref_graph_torch as T
+    from tfoptflow_b200 import model_pwcnet as M
+    torch.set_num_threads(os.cpu_count() or 1)
+    opts = M.pwcnet_options(a.params, search_range=a.search_range)
+
+    def corr_fn(c1, c2, up_flow, scaler, lvl):
+        warp = c2 if up_flow is None else T.dense_image_warp(c2, up_flow * scaler)
+        return T.cost_volume(c1, warp, a.search_range)
+
+    torch.manual_seed(1969)
+    model = M.ModelPWCNet(opts, corr_fn=corr_fn).eval()
+    x = torch.rand((a.batch, 2, a.height, a.width, 3))
+    times = []
+    t_end = time.perf_counter() + 200.0
+    with torch.no_grad():
+        for i in range(a.warmup + a.steps):
+            t0 = time.perf_counter()
+            model(x)
+            times.append(time.perf_counter() - t0)
+            if time.perf_counter() > t_end and len(times) >= 2:
+                break
+    timed = times[a.warmup:] if len(times) > a.warmup else times[-1:]
+    ms = 1e3 * sum(timed) / len(timed)
+    val = a.batch / (ms / 1e3)
+    cores = torch.get_num_threads()
+    line = _infer_line(a, a.gpus, val, ms, {
+        "impl": "reference", "steps": len(timed),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{a.batch} pair(s) per step, {len(timed)} timed steps, torch-CPU model with the op-for-op port "
+                                   f"of the reference operator graph, {cores} threads"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
+    print(json.dumps(line), flush=True)
     return 0
 
 
