@@ -19,6 +19,10 @@
 //     and 1/C on the accumulator fragments, which are scattered into a [pixel][81] staging tile; phase 4: the staged
 //     tile leaves as whole 16-byte vectors (32 pixels x 81 channels are contiguous in NHWC).
 //   * 92 KB of shared memory: two CTAs per SM overlap each other's gather and MMA phases.
+// That is the first variant (`fwd_mma16_kernel`, option mma_tile 0).  The default is the resident-halo variant further
+// down (`fwd_mma16_band_kernel`, namespace band): taller or narrower tiles per configuration, the four bilinear corners
+// kept packed until they are blended (16 loads in flight per thread), no tile-wide staging buffer - every warp stages
+// and writes its own (row, 16-pixel block) units - and search_range 8 as well as 4.
 #pragma once
 #include "common.cuh"
 
